@@ -1,0 +1,161 @@
+// device_types.h — parameter blocks passed by value to the kernels, and the launcher
+// prototypes capi.cu calls.  POD only; no torch / Eigen types.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "grid_geom.h"
+
+namespace fdem {
+
+// per-scan counters in device memory (zeroed at the start of every scan)
+enum Counter : int {
+  CNT_KEPT = 0,      // points surviving cropRange + cropZ
+  CNT_INSIDE = 1,    // kept points that fall inside the map (= valid sort keys)
+  CNT_CELLS = 2,     // touched cells (segments)
+  CNT_VOXELS = 3,    // voxelGrid(ANY) representatives
+  CNT_RAYS = 4,      // rays traced
+  CNT_RC_SKIP = 5,   // 1 when raycasting preconditions failed (sensor outside map)
+  CNT_COUNT = 8
+};
+
+// State that survives from scan to scan and is decided on the device (so a stream of
+// scans needs no host round trip).  Double buffered: scan s reads [s&1], the commit
+// kernel writes [(s+1)&1].
+struct DeviceState {
+  GridGeom geom;
+  uint32_t touched_count;  // valid entries in the touched-key list of the last scan with >=1 cell
+  uint32_t _pad;
+};
+
+enum InputFrame : int { INPUT_SENSOR_FRAME = 0, INPUT_MAP_FRAME = 1 };
+
+// everything K1 needs for one scan (fastdem::Config + the two transforms, pre-cast on the
+// host exactly as the reference casts them: Isometry3d::matrix().cast<float>(),
+// nanopcl/core/transform.hpp:68-82; (T_world_base*T_base_sensor).rotation().cast<float>(),
+// fastdem/src/fastdem.cpp:182-183)
+struct PreprocessParams {
+  const float4* xyzw;
+  const float* intensity;  // unused by K1; carried for symmetry
+  const float* cov9;       // optional caller-provided sensor-frame covariances (N x 9, col-major)
+  const float* var_z;      // optional (map-frame input): cloud.covariance(i)(2,2)
+  uint32_t n;
+  int32_t input_frame;
+  float T1[16];  // T_base_sensor as Matrix4f, column-major
+  float T2[16];  // T_world_base as Matrix4f, column-major
+  float R[9];    // rotation of T_world_base*T_base_sensor, column-major
+  double robot_x, robot_y;
+  float z_min, z_max, range_min_sq, range_max_sq;
+  int32_t sensor_type;
+  float lidar_range_noise, lidar_angular_noise;  // already fabs()'d
+  float rgbd_a, rgbd_b, rgbd_c, rgbd_k;
+  float constant_variance;  // uncertainty^2
+  int32_t local_mode;
+  uint32_t invalid_key;  // = number of cells in this handle's slab
+};
+
+// pointers to every layer the estimator kernel reads or writes (null when absent)
+struct EstLayers {
+  float *elevation, *elevation_min, *elevation_max;
+  float *variance, *n_points, *upper_bound, *lower_bound;
+  float *obstacle, *intensity, *color;
+  float *kalman_p, *sample_mean, *sample_m2;
+  float* p2_q[5];
+  float* p2_n[5];
+};
+
+struct EstimateParams {
+  const uint32_t* sorted_keys;
+  const uint32_t* sorted_vals;
+  const float4* pm;        // K1 output: map-frame x, y, z, var_z per input point
+  const float* intensity;  // input channel (null when the cloud has none)
+  const uint8_t* rgb;      // input channel (null when the cloud has none)
+  uint32_t* touched_keys;  // out: key at segment heads, invalid_key elsewhere
+  float* touched_minz;     // out (optional): per-scan min_z at segment heads
+  uint32_t n_sorted;
+  uint32_t invalid_key;
+  int32_t estimation_type;
+  float kalman_min_variance, kalman_max_variance, kalman_process_noise;
+  float p2_dn[5];  // already clamped + monotonised (quantile_estimation.hpp:83-94)
+  int32_t p2_marker;
+  float p2_max_sample_count;
+  EstLayers L;
+};
+
+constexpr int kMaxLayers = 48;
+struct LayerTable {
+  float* ptr[kMaxLayers];
+  int32_t count;
+  int32_t basic[3];  // indices of elevation, elevation_min, elevation_max
+};
+
+struct CommitParams {
+  double robot_x, robot_y;
+  int32_t local_mode;
+  int32_t clear_policy;
+  uint32_t invalid_key;
+  float* obstacle;
+  const uint32_t* touched_keys;
+};
+
+struct RaycastParams {
+  float origin[3];
+  float height_conflict_threshold, log_odds_observed, log_odds_ghost, log_odds_max,
+      clear_threshold;
+  float* elevation;
+  float* raycasting;    // per-scan min ray height (NaN = not traversed)
+  float* logodds;       // _visibility_logodds
+  float* ghost_removal;
+  uint32_t* ray_min_enc;  // scratch, one u32 per cell: order-preserving encoding for atomicMin
+  uint32_t* hits;         // scratch, one u32 per cell: observed-evidence hit counts
+};
+
+// ── launchers (kernels.cu) ───────────────────────────────────────────────────
+struct LaunchCounter {
+  int64_t mine = 0;     // kernels written in this repo
+  int64_t library = 0;  // CUB kernels (radix sort passes)
+};
+
+void launch_fill(float* dst, size_t n, float v, cudaStream_t s, LaunchCounter& lc);
+void launch_fill_u32(uint32_t* dst, size_t n, uint32_t v, cudaStream_t s, LaunchCounter& lc);
+void launch_any_not_nan(const float* src, size_t n, uint32_t* flag, cudaStream_t s,
+                        LaunchCounter& lc);
+void launch_clear_cell(const LayerTable& lt, int64_t lin, cudaStream_t s, LaunchCounter& lc);
+void launch_preprocess_bin(const PreprocessParams& p, const DeviceState* st_in, uint32_t* counters,
+                           float4* pm, uint32_t* keys, uint32_t* vals, cudaStream_t s,
+                           LaunchCounter& lc);
+void launch_commit(const CommitParams& p, const DeviceState* st_in, DeviceState* st_out,
+                   const uint32_t* counters, const LayerTable& lt, cudaStream_t s,
+                   LaunchCounter& lc);
+void launch_segreduce_estimate(const EstimateParams& p, const uint32_t* counters_ro,
+                               uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_move_only(const DeviceState* st_in, DeviceState* st_out, double x, double y,
+                      int clear_policy, const LayerTable& lt, uint32_t* moved_flag, cudaStream_t s,
+                      LaunchCounter& lc);
+
+// voxelGrid(ANY) + raycasting (kernels_raycast.cu)
+void launch_voxel_keys(const float4* pm, uint32_t n, float inv_voxel, uint64_t* keys,
+                       uint32_t* vals, cudaStream_t s, LaunchCounter& lc);
+void launch_voxel_select(const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                         uint32_t* counters, uint32_t* out_sel, cudaStream_t s, LaunchCounter& lc);
+void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const float4* pts,
+                         const uint32_t* sel, const uint32_t* n_sel_dev, uint32_t n_max,
+                         uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,
+                            const uint32_t* counters, size_t n_cells, cudaStream_t s,
+                            LaunchCounter& lc);
+void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
+                         cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
+
+// radix sorts (sort.cu; CUB DeviceRadixSort — stable, which the tie-breaks rely on)
+size_t sort_pairs_u32_temp_bytes(uint32_t n, int end_bit);
+cudaError_t sort_pairs_u32(void* temp, size_t temp_bytes, const uint32_t* kin, uint32_t* kout,
+                           const uint32_t* vin, uint32_t* vout, uint32_t n, int end_bit,
+                           cudaStream_t s, LaunchCounter& lc);
+size_t sort_pairs_u64_temp_bytes(uint32_t n, int end_bit);
+cudaError_t sort_pairs_u64(void* temp, size_t temp_bytes, const uint64_t* kin, uint64_t* kout,
+                           const uint32_t* vin, uint32_t* vout, uint32_t n, int end_bit,
+                           cudaStream_t s, LaunchCounter& lc);
+
+}  // namespace fdem

@@ -1,0 +1,262 @@
+/* fastdem_b200.h — C-ABI of libfastdem_b200.so
+ *
+ * The drop-in boundary for ONE path of Ikhyeon-Cho/FastDEM (reference @ 30d371e):
+ * the per-scan point-cloud -> elevation-grid integration,
+ *   fastdem::FastDEM::integrate            fastdem/include/fastdem/fastdem.hpp:115-120
+ *   fastdem::ElevationMapping::update      fastdem/include/fastdem/mapping/elevation_mapping.hpp:41-42
+ *   fastdem::applyRaycasting               fastdem/include/fastdem/postprocess/raycasting.hpp:49-51
+ * executed as hand-written CUDA for sm_100a on a device-resident map.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API.  This header
+ * is what a binding for that API talks to (plain C, opaque handles, pointers and
+ * sizes, int status, no exceptions, no torch/Eigen types).  The reference-facing
+ * C++ shell (fastdem_b200/host/fastdem/..., same class names as the reference) and
+ * the Python mirror (fastdem_b200/api.py) are both thin layers over these calls;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns fdem_status (0 = OK) unless noted; on error
+ *     fdem_last_error() holds a message (thread-local).  Nothing throws.
+ *   - one caller at a time per handle, like the reference ("not thread-safe",
+ *     fastdem.hpp:48-53).
+ *   - matrices (layers) are float32, rows x cols, COLUMN-MAJOR (linear = col*rows+row),
+ *     exactly nanogrid::Matrix = Eigen::MatrixXf (fastdem/src/io_npz.cpp:142-144).
+ *   - 4x4 transforms are double[16] COLUMN-MAJOR = Eigen::Isometry3d::matrix().data().
+ *   - point clouds: xyzw float32 N x 4 (w = 1; nanopcl::PointCloud::points(),
+ *     nanopcl/core/point_cloud.hpp:37-38), optional intensity float32 N, optional rgb
+ *     uint8 N x 3 (nanopcl::Color, core/types.hpp:46-52).  Pointers may be HOST or
+ *     DEVICE memory (detected with cudaPointerGetAttributes); host buffers are staged
+ *     through pinned memory on the mapper's stream.
+ *   - the CUDA device is fixed at fdem_map_create(); there is NO CPU fallback: without a
+ *     usable device every entry point fails with FDEM_ERR_CUDA.
+ */
+#ifndef FASTDEM_B200_H
+#define FASTDEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define FDEM_ABI_VERSION 1
+
+typedef int32_t fdem_status;
+enum {
+  FDEM_OK = 0,
+  FDEM_ERR_INVALID_ARGUMENT = 1, /* bad pointer / size / enum; also nanopcl voxelGrid's
+                                    std::invalid_argument (voxel_grid_impl.hpp:31-33) */
+  FDEM_ERR_CUDA = 2,             /* any CUDA runtime error (message has the string) */
+  FDEM_ERR_NO_LAYER = 3,         /* nanogrid::GridMap::get() on a missing layer */
+  FDEM_ERR_OUT_OF_MEMORY = 4,
+  FDEM_ERR_UNSUPPORTED = 5
+};
+
+/* fastdem::SensorType          fastdem/include/fastdem/config/sensor_model.hpp:10-14 */
+enum { FDEM_SENSOR_CONSTANT = 0, FDEM_SENSOR_LIDAR = 1, FDEM_SENSOR_RGBD = 2 };
+/* fastdem::MappingMode         fastdem/include/fastdem/config/mapping.hpp:8-11 */
+enum { FDEM_MODE_LOCAL = 0, FDEM_MODE_GLOBAL = 1 };
+/* fastdem::EstimationType      fastdem/include/fastdem/config/mapping.hpp:13-16 */
+enum { FDEM_EST_KALMAN = 0, FDEM_EST_P2QUANTILE = 1 };
+/* which layers GridMap::move() resets on the vacated rows/cols.  nanoGrid is not in the
+ * reference tree, so this is an explicit, documented choice (DESIGN.md "nanoGrid"). */
+enum { FDEM_MOVE_CLEAR_ALL_LAYERS = 0, FDEM_MOVE_CLEAR_BASIC_LAYERS = 1 };
+
+/* fastdem::Config, flattened    fastdem/include/fastdem/config/fastdem.hpp:21-37
+ * (+ config/mapping.hpp:20-47, config/sensor_model.hpp:18-37, config/postprocess.hpp:15-23).
+ * Field defaults = the reference's struct defaults; fdem_config_default() fills them. */
+typedef struct fdem_config {
+  /* config::PointFilter */
+  float z_min, z_max, range_min, range_max;
+  /* config::SensorModel */
+  int32_t sensor_type;
+  float lidar_range_noise, lidar_angular_noise;
+  float rgbd_normal_a, rgbd_normal_b, rgbd_normal_c, rgbd_lateral_factor;
+  float constant_uncertainty;
+  /* config::Mapping */
+  int32_t mode;
+  int32_t estimation_type;
+  float kalman_min_variance, kalman_max_variance, kalman_process_noise;
+  float p2_dn[5];
+  int32_t p2_elevation_marker;
+  float p2_max_sample_count;
+  /* config::Raycasting */
+  int32_t raycasting_enabled;
+  float rc_height_conflict_threshold, rc_log_odds_observed, rc_log_odds_ghost, rc_log_odds_max,
+      rc_clear_threshold;
+  /* restated-nanoGrid switch (see enum above) */
+  int32_t move_clear_policy;
+} fdem_config;
+
+/* What one integrate() did.  `integrated` is FastDEM::integrate's bool
+ * (fastdem/src/fastdem.cpp:125-128,137-138,161). */
+typedef struct fdem_scan_stats {
+  int64_t n_input;  /* points passed in                                         */
+  int64_t n_kept;   /* survived cropRange + cropZ (fastdem.cpp:175-176)          */
+  int64_t n_cells;  /* cells touched by rasterize (elevation_mapping.cpp:41-92)  */
+  int64_t n_voxels; /* ray_scan size after voxelGrid(ANY) (fastdem.cpp:156-157)  */
+  int32_t integrated;
+  int32_t _pad;
+} fdem_scan_stats;
+
+/* nanogrid::GridMap geometry accessors (getSize/getResolution/getLength/getPosition/
+ * getStartIndex), as of the last completed call. */
+typedef struct fdem_geometry {
+  int32_t rows, cols;
+  double resolution;
+  double length[2];
+  double position[2];
+  int32_t start_index[2];
+  /* row stripe held by this handle: logical rows [row_begin, row_end) of a rows x cols map.
+   * [0, rows) for an unsharded map. */
+  int32_t row_begin, row_end;
+} fdem_geometry;
+
+typedef struct fdem_map fdem_map;       /* fastdem::ElevationMap, device resident */
+typedef struct fdem_mapper fdem_mapper; /* fastdem::FastDEM bound to one map       */
+
+/* ── library ─────────────────────────────────────────────────────────────── */
+int32_t fdem_abi_version(void);
+const char* fdem_last_error(void);
+const char* fdem_status_string(fdem_status s);
+void fdem_config_default(fdem_config* cfg); /* = fastdem::Config{} */
+
+/* ── map: fastdem::ElevationMap  (fastdem/include/fastdem/elevation_map.hpp:65-177) ── */
+
+/* ElevationMap(width, height, resolution, frame) + setGeometry (elevation_map.hpp:105-116):
+ * size = round(length/resolution), basic layers elevation/elevation_min/elevation_max, all
+ * NaN.  `device` = CUDA ordinal.  `stream` = a cudaStream_t the map's work is ordered on
+ * (0 => the library creates its own non-blocking stream). */
+fdem_status fdem_map_create(float width, float height, float resolution, int32_t device,
+                            void* stream, fdem_map** out);
+/* One row stripe [row_begin,row_end) of the same logical map, for the multi-GPU GLOBAL
+ * configuration.  Only GLOBAL mapping is valid on a stripe. */
+fdem_status fdem_map_create_stripe(float width, float height, float resolution,
+                                   int32_t row_begin, int32_t row_end, int32_t device,
+                                   void* stream, fdem_map** out);
+fdem_status fdem_map_destroy(fdem_map* map);
+
+fdem_status fdem_map_get_geometry(fdem_map* map, fdem_geometry* out);
+/* GridMap::setPosition / setStartIndex (used by snapshot/load, elevation_map.hpp:166-167) */
+fdem_status fdem_map_set_position(fdem_map* map, double x, double y);
+fdem_status fdem_map_set_start_index(fdem_map* map, int32_t row, int32_t col);
+/* GridMap::move(position): circular-buffer shift, vacated rows/cols reset to NaN
+ * (call site fastdem/src/elevation_mapping.cpp:111-113).  *moved = 1 if the start index changed. */
+fdem_status fdem_map_move(fdem_map* map, double x, double y, int32_t clear_policy, int32_t* moved);
+/* GridMap::isInside / getIndex / getPosition (host-side geometry math, no device work) */
+fdem_status fdem_map_is_inside(fdem_map* map, double x, double y, int32_t* inside);
+fdem_status fdem_map_get_index(fdem_map* map, double x, double y, int32_t* row, int32_t* col,
+                               int32_t* inside);
+fdem_status fdem_map_get_cell_position(fdem_map* map, int32_t row, int32_t col, double* x,
+                                       double* y);
+
+/* GridMap::exists / add(name, fill) / getLayers */
+fdem_status fdem_map_layer_exists(fdem_map* map, const char* name, int32_t* exists);
+fdem_status fdem_map_layer_add(fdem_map* map, const char* name, float fill);
+fdem_status fdem_map_layer_count(fdem_map* map, int32_t* count);
+fdem_status fdem_map_layer_name(fdem_map* map, int32_t i, char* buf, int32_t cap);
+/* GridMap::get(layer) as a copy: dst/src are (row_end-row_begin) x cols float32 column-major,
+ * HOST or DEVICE memory. */
+fdem_status fdem_map_layer_download(fdem_map* map, const char* name, float* dst);
+fdem_status fdem_map_layer_upload(fdem_map* map, const char* name, const float* src);
+/* zero-copy view for torch / downstream kernels: device pointer to the layer slab */
+fdem_status fdem_map_layer_device_ptr(fdem_map* map, const char* name, float** dptr);
+/* GridMap::at(layer, index) read / write of a single cell (tests, clearAt fixtures) */
+fdem_status fdem_map_cell_get(fdem_map* map, const char* name, int32_t row, int32_t col, float* v);
+fdem_status fdem_map_cell_set(fdem_map* map, const char* name, int32_t row, int32_t col, float v);
+/* GridMap::clear(layer) / clearAll() (FastDEM::reset, fastdem/src/fastdem.cpp:26) /
+ * ElevationMap::clearAt (elevation_map.hpp:131-135) / ElevationMap::isEmpty (:123-125) */
+fdem_status fdem_map_clear(fdem_map* map, const char* name);
+fdem_status fdem_map_clear_all(fdem_map* map);
+fdem_status fdem_map_clear_at(fdem_map* map, int32_t row, int32_t col);
+fdem_status fdem_map_is_empty(fdem_map* map, int32_t* empty);
+fdem_status fdem_map_sync(fdem_map* map); /* wait for all queued work on the map's stream */
+void* fdem_map_stream(fdem_map* map);     /* the cudaStream_t work is ordered on */
+
+/* ── mapper: fastdem::FastDEM  (fastdem/include/fastdem/fastdem.hpp:55-156) ──────── */
+
+/* FastDEM(ElevationMap&, const Config&) (fastdem/src/fastdem.cpp:19-22): creates the
+ * estimator layers (Kalman::ensureLayers kalman_estimation.hpp:64-82 or
+ * P2Quantile::ensureLayers quantile_estimation.hpp:97-115) and `obstacle`
+ * (elevation_mapping.cpp:38).  The map must outlive the mapper (FastDEM holds a reference). */
+fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mapper** out);
+fdem_status fdem_mapper_destroy(fdem_mapper* m);
+/* the fluent setters (fastdem.cpp:28-66) collapsed into one call: re-creates the sensor
+ * model / ElevationMapping exactly as setMappingMode/setEstimatorType/setSensorModel do
+ * (missing estimator layers are added, existing data persists). */
+fdem_status fdem_mapper_set_config(fdem_mapper* m, const fdem_config* cfg);
+fdem_status fdem_mapper_get_config(fdem_mapper* m, fdem_config* out);
+
+/* FastDEM::integrate(cloud, T_base_sensor, T_world_base) (fastdem.cpp:122-162), synchronous:
+ * returns after the scan is in the map, *stats filled.  stats->integrated == 0 <=> the
+ * reference returns false (empty input / everything filtered). */
+fdem_status fdem_mapper_integrate(fdem_mapper* m, const float* xyzw, const float* intensity,
+                                  const uint8_t* rgb, size_t n, const double T_base_sensor[16],
+                                  const double T_world_base[16], fdem_scan_stats* stats);
+/* Same work, queued on the map's stream without waiting; results of scan k are read with
+ * fdem_mapper_wait().  Lets the caller keep the GPU fed (no host round trip per scan).
+ * Device input buffers must stay valid until the matching wait. */
+fdem_status fdem_mapper_integrate_async(fdem_mapper* m, const float* xyzw, const float* intensity,
+                                        const uint8_t* rgb, size_t n,
+                                        const double T_base_sensor[16],
+                                        const double T_world_base[16]);
+/* blocks until every queued scan is done; *stats (optional) = the LAST scan's stats. */
+fdem_status fdem_mapper_wait(fdem_mapper* m, fdem_scan_stats* stats);
+
+/* ElevationMapping::update(cloud, robot_position) (elevation_mapping.cpp:110-125): points
+ * already in the map frame; var_z optional = cloud.covariance(i)(2,2) (null => cloud has no
+ * covariance channel => 0 => Kalman uses max_variance, kalman_estimation.hpp:112-113). */
+fdem_status fdem_mapper_update(fdem_mapper* m, const float* xyzw, const float* var_z,
+                               const float* intensity, const uint8_t* rgb, size_t n,
+                               double robot_x, double robot_y, fdem_scan_stats* stats);
+
+/* integrate() for a caller-provided SensorModel subclass (FastDEM::setSensorModel(unique_ptr),
+ * fastdem.hpp:80): cov9 = N x 9 float32 column-major sensor-frame covariances computed by the
+ * caller's computeCovariances() (sensors/sensor_model.hpp:76-85). */
+fdem_status fdem_mapper_integrate_with_cov(fdem_mapper* m, const float* xyzw, const float* cov9,
+                                           const float* intensity, const uint8_t* rgb, size_t n,
+                                           const double T_base_sensor[16],
+                                           const double T_world_base[16], fdem_scan_stats* stats);
+
+/* FastDEM::onScanPreprocessed payload (fastdem.cpp:139-141): the preprocessed cloud of the
+ * LAST integrate, compacted in input order.  Buffers are HOST memory sized for n_kept:
+ * xyzw [n_kept*4], cov9 [n_kept*9] (optional), src_index [n_kept] (optional). */
+fdem_status fdem_mapper_last_preprocessed(fdem_mapper* m, float* xyzw, float* cov9,
+                                          int32_t* src_index, int64_t* n_kept);
+/* FastDEM::onScanRasterized payload (fastdem.cpp:148-150, 200-214): one point per touched
+ * cell (cell centre x,y; z = min_z) of the LAST integrate.  xyz HOST [n_cells*3]; order is by
+ * ascending buffer linear index (the reference's order is hash order, i.e. unspecified). */
+fdem_status fdem_mapper_last_rasterized(fdem_mapper* m, float* xyz, int64_t* n_cells);
+
+/* ── stage-level entry points ─────────────────────────────────────────────── */
+
+/* fastdem::applyRaycasting(map, scan, sensor_origin, cfg) (fastdem/src/raycasting.cpp:218-249);
+ * scan in map frame, HOST or DEVICE. */
+fdem_status fdem_raycast(fdem_map* map, const float* xyzw, size_t n, const float sensor_origin[3],
+                         const fdem_config* cfg);
+/* nanopcl::filters::voxelGrid(cloud, voxel_size, VoxelMode::ANY) (voxel_grid_impl.hpp:30-236):
+ * out_index HOST [<= n] = selected source indices in voxel-key order; ties resolved as the
+ * oracle defines (sort on (key, index)). */
+fdem_status fdem_voxel_grid_any(fdem_map* map, const float* xyzw, size_t n, float voxel_size,
+                                uint32_t* out_index, int64_t* n_voxels);
+/* fastdem::applyInpainting(map, max_iterations, min_valid_neighbors, inplace)
+ * (fastdem/src/inpainting.cpp:21-67) */
+fdem_status fdem_inpaint(fdem_map* map, int32_t max_iterations, int32_t min_valid_neighbors,
+                         int32_t inplace);
+
+/* ── instrumentation ──────────────────────────────────────────────────────── */
+/* number of kernels THIS library launched since the handle was created (bench.py's
+ * gpu_launches) */
+fdem_status fdem_mapper_launch_count(fdem_mapper* m, int64_t* launches);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTDEM_B200_H */

@@ -1,0 +1,35 @@
+"""-m gpu: the CUDA path against the CPU oracle on the BASELINE.json workloads, scan by scan,
+every layer.  Bit-exact NaN masks / counts / colour bits,
+1e-5 relative on heights and variances (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from fastdem_b200 import synthetic as syn
+from parity_utils import compare_maps, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,n_scans", [
+    ("tiny", 12),
+    ("c1_vlp16_local", 8),       # BASELINE configs[0]: the reference's CPU-runnable case
+    ("c2_lidar64_local", 6),     # configs[1]: the bench workload
+    ("c3_rgbd_p2", 7),           # configs[2]: RGBD model + P2 (needs > 5 scans to leave phase 1)
+])
+def test_workload_parity(fdem, name, n_scans):
+    wl = syn.WORKLOADS[name]
+    gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, n_scans)
+    report = compare_maps(gmap, omap)
+    touched = int(np.isfinite(omap.get("elevation")).sum())
+    assert touched > 0
+    print(f"{name}: {touched} cells with elevation; cells differing in bits per layer: "
+          f"{ {k: v for k, v in report.items() if v} }")
+
+
+def test_c1_basic_layer_policy(fdem):
+    """move() clearing policy switch: BASIC layers only, same check."""
+    wl = syn.WORKLOADS["c1_vlp16_local"]
+    cfg = wl.config()
+    cfg.move_clear_policy = 1
+    gmap, omap, *_ = run_pair(fdem, wl, 8, cfg)
+    compare_maps(gmap, omap)
