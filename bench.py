@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — scans/s and Mpoints/s of FastDEM::integrate() on B200, beside the CPU path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" is one integrate() of one synthetic scan of the workload (default: BASELINE.json
+configs[1], 64-beam LiDAR 131K pts, 30x30 m @ 0.05 m, Kalman, LOCAL).  One JSON line on
+stdout (rank 0).
+
+  value    scans/s with the scan already resident in HBM (device pointers through the C-ABI,
+           scans queued back to back, no host sync inside the timed region).  L2 is flushed
+           (256 MiB fill) before every timed step, each step is bracketed by CUDA events on
+           the stream the kernels run on, and ms_per_step = mean over the K steps.
+  e2e      the same metric through the public API with HOST (pinned) buffers: every step
+           copies the scan host->device, runs integrate() synchronously and reads the scan
+           stats + committed geometry back.  Wall clock, barrier + synchronize on both sides.
+  roofline the slowest pipeline stage, its algorithmic bytes over
+           its mean device time, against the MEASURED copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the CPU oracle (a line-by-line restatement of the reference path; the
+           reference itself cannot be built here — no Eigen / nanoGrid) on 1 host core.
+
+N > 1 (torchrun): LOCAL mapping does not shard — each rank integrates its own
+robot's scan stream into its own map ("replicas", weak scaling, no data-path collective);
+torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the time.
+`--workload c5_global` instead row-stripes ONE global map over the ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+
+import numpy as np
+
+
+def _peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(wl, n_points, stats_list, has_i, has_c, p2):
+    """B = N*b_pt + C*b_cell + C_prev*4, split per pipeline stage.
+    Compulsory traffic only — no sort scratch, no intermediate copies."""
+    b_pt = 16 + (4 if has_i else 0) + (3 if has_c else 0)
+    b_cell = (124 if p2 else 76) + (8 if has_i else 0) + (4 if has_c else 0)
+    C = statistics.mean(s.n_cells for s in stats_list) if stats_list else 0.0
+    Nv = statistics.mean(s.n_kept for s in stats_list) if stats_list else 0.0
+    per_stage = {
+        "preprocess_bin": n_points * 16.0,                       # every input point read once
+        "commit_move_clear": C * 4.0,                            # last scan's obstacle cells
+        "sort_by_cell": 0.0,                                     # pure scratch traffic
+        "segreduce_estimate": C * b_cell + Nv * (b_pt - 16.0),   # cell state + per-point channels
+    }
+    return per_stage, n_points * b_pt + C * b_cell + C * 4.0
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  It cannot be
+    built here (no Eigen, nanoGrid un-vendored), so this times the oracle port — a
+    line-by-line restatement incl. the by-value cloud copy, 36-byte covariances and the
+    unordered_map rasteriser — single-threaded, exactly like the reference path."""
+    if rank != 0:
+        return None
+    import oracle_binding as ob
+    from fastdem_b200 import synthetic as syn
+    cfg = wl.config()
+    omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    odem = ob.OracleFastDEM(omap, cfg)
+    ring = [syn.make_scan(wl, k) for k in range(min(8, args.warmup + args.steps))]
+    k = 0
+    for _ in range(args.warmup):
+        s = ring[k % len(ring)]
+        odem.integrate(s["xyzw"], *pose_for(wl, k), s["intensity"], s["rgb"])
+        k += 1
+    total = 0.0
+    budget_s = 120.0
+    done = 0
+    for _ in range(args.steps):
+        s = ring[k % len(ring)]
+        _, _, el = odem.integrate(s["xyzw"], *pose_for(wl, k), s["intensity"], s["rgb"])
+        total += el
+        k += 1
+        done += 1
+        if total > budget_s:
+            break
+    n = wl.points_per_scan
+    ms = 1e3 * total / max(done, 1)
+    val = done / total
+    return {
+        "impl": "reference", "metric": "integrate_scans_per_sec", "value": val, "unit": "scans/s",
+        "mpoints_per_s": val * n / 1e6, "n_gpus": world, "steps": done, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (cell state) / f64 (geometry)", "data": "synthetic",
+        "config": {"workload": wl.name, "description": wl.description, "points_per_scan": n},
+        "cpu_baseline": {"value": val, "unit": "scans/s", "cores": 1, "kind": "port",
+                         "sample": f"{done} scans of {wl.name} on 1 host core (reference path is single-threaded; "
+                                   f"{os.cpu_count()} cores on the box)"},
+        "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def pose_for(wl, k):
+    from fastdem_b200 import synthetic as syn
+    return syn.pose(wl, k)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_lidar64_local")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from fastdem_b200 import synthetic as syn
+    wl = syn.WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        out = run_reference(args, wl, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+
+    args.warmup = max(args.warmup, 3)
+    import torch
+    import torch.distributed as dist
+    import fastdem_b200 as fd
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}), flush=True)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    sharded = wl.name == "c5_global" and world > 1
+    cfg = wl.config()
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        if sharded:
+            from fastdem_b200.sharded import stripe_bounds
+            rows = int(round(wl.map_width / wl.resolution))
+            r0, r1 = stripe_bounds(rows, world, rank)
+            gmap = fd.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map", device=local_rank,
+                                   stream=stream.cuda_stream, row_stripe=(r0, r1))
+        else:
+            gmap = fd.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map", device=local_rank,
+                                   stream=stream.cuda_stream)
+        dem = fd.FastDEM(gmap, cfg)
+
+        # distinct scans, generated once; replicas shift the scan index so ranks differ
+        n_ring = 8 if wl.points_per_scan <= 400_000 else 4
+        base = 0 if sharded else 1000 * rank
+        host = [syn.make_scan(wl, base + k) for k in range(n_ring)]
+        n = wl.points_per_scan
+        has_i, has_c = host[0]["intensity"] is not None, host[0]["rgb"] is not None
+        dev_scans, pin_scans = [], []
+        for s in host:
+            d = dict(xyzw=torch.from_numpy(s["xyzw"]).to(dev),
+                     intensity=None if not has_i else torch.from_numpy(s["intensity"]).to(dev),
+                     rgb=None if not has_c else torch.from_numpy(s["rgb"]).to(dev))
+            dev_scans.append(fd.PointCloud(d["xyzw"], d["intensity"], d["rgb"]))
+            p = dict(xyzw=torch.from_numpy(s["xyzw"]).pin_memory(),
+                     intensity=None if not has_i else torch.from_numpy(s["intensity"]).pin_memory(),
+                     rgb=None if not has_c else torch.from_numpy(s["rgb"]).pin_memory())
+            pc = fd.PointCloud()
+            pc.xyzw = p["xyzw"].numpy()
+            pc.intensity = None if not has_i else p["intensity"].numpy()
+            pc.color = None if not has_c else p["rgb"].numpy()
+            pc._pinned = p
+            pin_scans.append(pc)
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def barrier():
+            torch.cuda.synchronize(dev)
+            if distributed:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        # ── warm-up (also sizes every scratch buffer) ──
+        k = 0
+        for _ in range(args.warmup):
+            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            k += 1
+        dem.wait()
+
+        # ── timed region: device-resident inputs, per-step events, L2 flushed before each ──
+        l0, lib0 = dem.launch_count(), dem.library_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        stats_ring = []
+        for i in range(args.steps):
+            if not args.no_flush:
+                flush_buf.fill_(i & 0xFF)
+            ev[i][0].record(stream)
+            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            ev[i][1].record(stream)
+            k += 1
+        last = dem.wait()
+        barrier()
+        clocks = sampler.stop()
+        launches = dem.launch_count() - l0
+        lib_launches = dem.library_launch_count() - lib0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+
+        # ── stage attribution pass (separate from the timed region: bracketing every stage
+        #    with events costs ~2.7 us per event and forces one launch per kernel) ──
+        dem.set_stage_timing(True)
+        for i in range(min(args.steps, 64)):
+            if not args.no_flush:
+                flush_buf.fill_(i & 0xFF)
+            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            k += 1
+        dem.wait()
+        stage_ms, stage_scans = dem.stage_times()
+        dem.set_stage_timing(False)
+
+        # per-scan statistics for the roofline's algorithmic bytes (a few synchronous scans)
+        for j in range(min(8, args.steps)):
+            stats_ring.append(dem.integrate_stats(dev_scans[k % n_ring], *syn.pose(wl, base + k)))
+            k += 1
+
+        # ── e2e: public API, pinned host buffers, synchronous, H2D + D2H inside ──
+        e2e_steps = args.steps
+        for _ in range(3):
+            dem.integrate_stats(pin_scans[k % n_ring], *syn.pose(wl, base + k))
+            k += 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dem.integrate_stats(pin_scans[k % n_ring], *syn.pose(wl, base + k))
+            k += 1
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    # ── reduce over ranks: max time ──
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    units = args.steps * (1 if sharded else world)   # scans all ranks processed
+    value = units / (total_ms / 1e3)
+    e2e_value = (e2e_steps * (1 if sharded else world)) / e2e_s
+
+    out = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        per_stage_bytes, total_bytes = algorithmic_bytes(
+            wl, n, stats_ring, has_i, has_c, cfg.estimation_type == fd.EST_P2QUANTILE)
+        stage_avg = {s: (ms / max(stage_scans, 1)) for s, ms in stage_ms.items()}
+        timed = {s: v for s, v in stage_avg.items() if s != "h2d"}
+        dominant = max(timed, key=timed.get)
+        dom_ms = timed[dominant]
+        dom_bytes = per_stage_bytes.get(dominant, 0.0)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {
+            "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes,
+            "kernel_ms": dom_ms,
+            "stage_ms": stage_avg,
+            "stage_ms_note": "separate pass, one launch per kernel, ~2.7 us event overhead inside each stage",
+            "stage_share": {s: v / max(sum(timed.values()), 1e-12) for s, v in timed.items()},
+            "pipeline": {"algorithmic_bytes_per_scan": total_bytes,
+                         "achieved": total_bytes / ((total_ms / args.steps) * 1e-3) / 1e9,
+                         "frac": total_bytes / ((total_ms / args.steps) * 1e-3) / 1e9 / peak},
+        }
+
+        # ── CPU baseline: the oracle on one host core, bounded sample ──
+        import oracle_binding as ob
+        omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+        odem = ob.OracleFastDEM(omap, cfg)
+        cpu_total, cpu_n, kk = 0.0, 0, 0
+        for _ in range(2):
+            s = host[kk % n_ring]
+            odem.integrate(s["xyzw"], *syn.pose(wl, base + kk), s["intensity"], s["rgb"])
+            kk += 1
+        while cpu_total < args.cpu_seconds and cpu_n < 2000:
+            s = host[kk % n_ring]
+            _, _, el = odem.integrate(s["xyzw"], *syn.pose(wl, base + kk), s["intensity"], s["rgb"])
+            cpu_total += el
+            cpu_n += 1
+            kk += 1
+        cpu_val = cpu_n / cpu_total
+
+        h2d = n * (16 + (4 if has_i else 0) + (3 if has_c else 0))
+        out = {
+            "metric": "integrate_scans_per_sec", "value": value, "unit": "scans/s",
+            "mpoints_per_s": value * n / 1e6,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": "f32 (cell state) / f64 (geometry)", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description, "points_per_scan": n,
+                       "map_cells": int(round(wl.map_width / wl.resolution)) * int(round(wl.map_height / wl.resolution)),
+                       "parallelism": ("row-stripes x%d" % world) if sharded else ("replicas x%d" % world),
+                       "l2": "inputs device-resident; 256 MiB L2 flush before every timed step" if not args.no_flush else "no flush",
+                       "scan_ring": n_ring},
+            "e2e": {"value": e2e_value, "unit": "scans/s", "mpoints_per_s": e2e_value * n / 1e6,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32 + 88,
+                    "how": "fdem_mapper_integrate() on pinned host buffers, synchronous, wall clock"},
+            "gpu_launches": int(launches), "library_launches": int(lib_launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_val, "unit": "scans/s", "cores": 1, "kind": "port",
+                             "ms_per_scan": 1e3 / cpu_val,
+                             "sample": f"{cpu_n} scans of {wl.name}, oracle port (-O3), 1 of {os.cpu_count()} host cores; "
+                                       "the reference path is single-threaded"},
+            "last_scan": {"n_kept": int(last.n_kept), "n_cells": int(last.n_cells)},
+        }
+        print(json.dumps(out), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

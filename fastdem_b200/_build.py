@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 BUILD = REPO / "build"
 LIB = PKG_DIR / "libfastdem_b200.so"
 
-SOURCES = ["kernels.cu", "kernels_raycast.cu", "sort.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "kernels_tile.cu", "kernels_raycast.cu", "sort.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

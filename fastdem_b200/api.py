@@ -562,6 +562,25 @@ class FastDEM:
         check(self._lib.fdem_mapper_last_rasterized(self._h, xyz.ctypes.data, C.byref(nc)))
         return PointCloud(xyz[:nc.value], frame_id=self._map.getFrameId())
 
+    def set_cell_sort(self, mode: int) -> None:
+        """capi.CELL_SORT_TILE (default) or capi.CELL_SORT_GLOBAL; results are identical."""
+        check(self._lib.fdem_mapper_set_cell_sort(self._h, mode))
+
+    def set_stage_timing(self, enabled: bool) -> None:
+        check(self._lib.fdem_mapper_set_stage_timing(self._h, 1 if enabled else 0))
+
+    def stage_times(self):
+        """-> ({stage: total device ms}, n_scans) accumulated since the last call."""
+        ms = (C.c_double * len(capi.STAGE_NAMES))()
+        n = C.c_int64()
+        check(self._lib.fdem_mapper_stage_times(self._h, ms, C.byref(n)))
+        return dict(zip(capi.STAGE_NAMES, list(ms))), n.value
+
+    def library_launch_count(self) -> int:
+        v = C.c_int64()
+        check(self._lib.fdem_mapper_library_launch_count(self._h, C.byref(v)))
+        return v.value
+
     def launch_count(self) -> int:
         v = C.c_int64()
         check(self._lib.fdem_mapper_launch_count(self._h, C.byref(v)))

@@ -16,6 +16,9 @@ SENSOR_CONSTANT, SENSOR_LIDAR, SENSOR_RGBD = 0, 1, 2
 MODE_LOCAL, MODE_GLOBAL = 0, 1
 EST_KALMAN, EST_P2QUANTILE = 0, 1
 MOVE_CLEAR_ALL_LAYERS, MOVE_CLEAR_BASIC_LAYERS = 0, 1
+CELL_SORT_TILE, CELL_SORT_GLOBAL = 0, 1
+STAGE_NAMES = ["h2d", "preprocess_bin", "commit_move_clear", "sort_by_cell", "segreduce_estimate",
+               "voxel_raycast"]
 
 
 class FdemConfig(C.Structure):
@@ -109,6 +112,10 @@ SIGNATURES = {
     "fdem_voxel_grid_any": (_ST, [_P, _f32p, C.c_size_t, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]),
     "fdem_inpaint": (_ST, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
+    "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
+    "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),
+    "fdem_mapper_set_cell_sort": (_ST, [_P, C.c_int32]),
+    "fdem_mapper_stage_times": (_ST, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -78,7 +79,6 @@ struct fdem_map {
   GridGeom geom{};            // host mirror; valid when !geom_stale
   bool geom_stale = false;    // async scans in flight may have moved the window
   DeviceState* d_state = nullptr;  // [2]
-  int parity = 0;
   size_t cells = 0;           // rows_local * cols
   std::vector<Layer> layers;
   // touched-cell list of the last observing scan (obstacle reset)
@@ -91,9 +91,38 @@ struct fdem_map {
   uint32_t* d_hits = nullptr;
   // small scratch
   uint32_t* d_flag = nullptr;
-  ScanResult* h_result = nullptr;  // pinned
+  ScanResult* h_result = nullptr;  // pinned + mapped: the publish kernel writes it directly
+  uint32_t* d_result_host = nullptr;  // device-side alias of h_result
   LaunchCounter lc;
 };
+
+namespace {
+// one scan's kernel arguments, kept alive in the mapper so graph nodes can be patched in place
+struct ScanLaunch {
+  PreprocessParams pp;
+  CommitParams cp;
+  ScatterParams sp;
+  EstimateParams ep;
+  LayerTable lt;
+  TileBuffers tb;
+  const DeviceState* st_cur;
+  DeviceState* st_next;
+  uint32_t* counters;
+  float4* pm;
+  uint32_t* keys;
+  uint32_t* vals;
+  uint32_t* host_out;
+  PublishArgs pub;
+};
+enum { GN_K1 = 0, GN_K2, GN_SCATTER, GN_K3T, GN_COUNT };
+struct ScanGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node[GN_COUNT] = {};
+  ScanLaunch cached{};
+  bool valid = false;
+};
+}  // namespace
 
 struct fdem_mapper {
   fdem_map* map = nullptr;
@@ -114,6 +143,20 @@ struct fdem_mapper {
   uint32_t last_n = 0;
   bool last_had_work = false;
   bool pending = false;  // async scans queued since the last wait
+  // tile path (2-level sort-by-cell); global CUB sort kept as the alternative path
+  bool use_tile = true;
+  bool use_graph = true;   // launch the tile pipeline as one CUDA graph (FDEM_GRAPH=0 disables)
+  bool counters_dirty = true;
+  ScanLaunch launch{};
+  ScanGraph sg;
+  bool tile_dirty = true;  // L1 scratch must be zeroed before the next scan
+  TileBuffers tb{};
+  // optional per-stage device timing (bench / profiling)
+  bool stage_timing = false;
+  std::vector<cudaEvent_t> ev_pool;               // free events
+  std::vector<std::vector<cudaEvent_t>> ev_scans;  // FDEM_STAGE_COUNT+1 events per in-flight scan
+  double stage_ms[FDEM_STAGE_COUNT] = {0, 0, 0, 0, 0, 0};
+  int64_t stage_scans = 0;
 };
 
 namespace {
@@ -179,7 +222,7 @@ fdem_status refresh_geometry(fdem_map* m) {
   if (!m->geom_stale) return FDEM_OK;
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
   DeviceState st;
-  FDEM_CUDA_TRY(cudaMemcpy(&st, m->d_state + m->parity, sizeof(st), cudaMemcpyDeviceToHost));
+  FDEM_CUDA_TRY(cudaMemcpy(&st, m->d_state, sizeof(st), cudaMemcpyDeviceToHost));
   m->geom = st.geom;
   m->geom_stale = false;
   return FDEM_OK;
@@ -189,8 +232,7 @@ fdem_status push_state(fdem_map* m, uint32_t touched_count) {
   DeviceState st{};
   st.geom = m->geom;
   st.touched_count = touched_count;
-  FDEM_CUDA_TRY(cudaMemcpyAsync(m->d_state + m->parity, &st, sizeof(st), cudaMemcpyHostToDevice,
-                                m->stream));
+  FDEM_CUDA_TRY(cudaMemcpyAsync(m->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, m->stream));
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
   return FDEM_OK;
 }
@@ -276,6 +318,8 @@ void free_scratch(fdem_mapper* mp) {
   cudaFree(mp->d_svkeys);
   cudaFree(mp->d_sel);
   cudaFree(mp->d_sort_temp);
+  cudaFree(mp->tb.records);
+  mp->tb.records = nullptr;
   mp->d_in_xyzw = nullptr; mp->d_in_intensity = nullptr; mp->d_in_rgb = nullptr;
   mp->d_in_aux = nullptr; mp->d_pm = nullptr; mp->d_keys = mp->d_vals = nullptr;
   mp->d_skeys = mp->d_svals = nullptr; mp->d_vkeys = mp->d_svkeys = nullptr;
@@ -311,6 +355,7 @@ fdem_status ensure_capacity(fdem_mapper* mp, size_t n) {
   }
   FDEM_CUDA_TRY(cudaMalloc(&mp->d_sort_temp, temp));
   mp->sort_temp_bytes = temp;
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.records, cap * sizeof(CellRecord)));
   mp->cap = cap;
   // the touched list lives in the map and must hold one entry per sorted element
   if (m->touched_cap < cap) {
@@ -374,8 +419,34 @@ EstLayers est_layers(fdem_map* m) {
 }
 
 fdem_status raycast_device(fdem_map* m, const fdem_config& cfg, const float origin[3],
-                           const float4* pts, const uint32_t* sel, const uint32_t* n_sel_dev,
+                           const float4* pts, const uint32_t* sel, const DeviceState* st,
                            uint32_t n_max, uint32_t* counters);
+fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s);
+
+cudaEvent_t take_event(fdem_mapper* mp) {
+  if (!mp->ev_pool.empty()) {
+    cudaEvent_t e = mp->ev_pool.back();
+    mp->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// fold finished scans' stage events into the accumulators (stream must be idle)
+void drain_stage_events(fdem_mapper* mp) {
+  for (auto& evs : mp->ev_scans) {
+    for (int st = 0; st < FDEM_STAGE_COUNT; ++st) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, evs[st], evs[st + 1]) == cudaSuccess) mp->stage_ms[st] += ms;
+    }
+    ++mp->stage_scans;
+    for (cudaEvent_t e : evs) mp->ev_pool.push_back(e);
+  }
+  mp->ev_scans.clear();
+  (void)cudaGetLastError();
+}
 
 // ── one scan: K1 -> K2 -> sort -> K3 (-> voxel + raycast) -> result D2H ─────────
 struct ScanInputs {
@@ -403,6 +474,16 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
                  "LOCAL mapping is not valid on a row stripe");
 
   FDEM_TRY(ensure_capacity(mp, n));
+  std::vector<cudaEvent_t>* evs = nullptr;
+  if (mp->stage_timing) {
+    mp->ev_scans.emplace_back();
+    evs = &mp->ev_scans.back();
+    for (int i = 0; i <= FDEM_STAGE_COUNT; ++i) evs->push_back(take_event(mp));
+  }
+  auto mark = [&](int boundary) {
+    if (evs) cudaEventRecord((*evs)[boundary], s);
+  };
+  mark(FDEM_STAGE_H2D);
   // layers the cloud's channels need (updateIntensity / updateColor add them lazily,
   // elevation_mapping.cpp:155,169)
   if (in.intensity) FDEM_TRY(ensure_layer(m, "intensity", kNaN));
@@ -451,38 +532,58 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   pp.constant_variance = cfg.constant_uncertainty * cfg.constant_uncertainty;
   pp.local_mode = cfg.mode == FDEM_MODE_LOCAL ? 1 : 0;
   pp.invalid_key = static_cast<uint32_t>(m->cells);
+  const bool tile = mp->use_tile;
+  pp.bucket_count = tile ? mp->tb.bucket_count : nullptr;
+  pp.write_vals = tile ? 0 : 1;
+  if (tile && mp->tile_dirty) {
+    // first scan / after a failed scan: the L1 scratch K3t normally re-arms must be zero
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_count, 0, mp->tb.n_buckets * sizeof(uint32_t), s));
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_cursor, 0, mp->tb.n_buckets * sizeof(uint32_t), s));
+    mp->tile_dirty = false;
+  }
 
-  const DeviceState* st_in = m->d_state + m->parity;
-  DeviceState* st_out = m->d_state + (m->parity ^ 1);
+  const DeviceState* st_in = m->d_state;     // current (committed) state
+  DeviceState* st_out = m->d_state + 1;      // this scan's state; publish makes it current
 
-  FDEM_CUDA_TRY(cudaMemsetAsync(mp->d_counters, 0, CNT_COUNT * sizeof(uint32_t), s));
-  launch_preprocess_bin(pp, st_in, mp->d_counters, mp->d_pm, mp->d_keys, mp->d_vals, s, m->lc);
-
+  if (mp->counters_dirty) {
+    // first scan / after a failed scan; afterwards the publish kernel re-arms the counters
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->d_counters, 0, CNT_COUNT * sizeof(uint32_t), s));
+    mp->counters_dirty = false;
+  }
   if (m->obstacle_full_clear) {
     // obstacle was uploaded / edited by the caller: fall back to the reference's whole-layer
-    // clear (elevation_mapping.cpp:146) until a scan with observations has gone through
+    // clear (elevation_mapping.cpp:146) until a scan with observations has gone through.
+    // Done unconditionally: if this scan ends up without observations the reference would
+    // not clear, but then the layer content was caller-provided and undefined for the path.
     float* ob = layer_ptr(m, "obstacle");
-    if (ob) {
-      // done unconditionally: if this scan ends up without observations the reference would
-      // not clear, but then the layer content was caller-provided and undefined for the path
-      launch_fill(ob, m->cells, kNaN, s, m->lc);
-    }
+    if (ob) launch_fill(ob, m->cells, kNaN, s, m->lc);
   }
-  CommitParams cp{};
-  cp.robot_x = in.robot_x;
-  cp.robot_y = in.robot_y;
-  cp.local_mode = pp.local_mode;
-  cp.clear_policy = cfg.move_clear_policy;
-  cp.invalid_key = pp.invalid_key;
-  cp.obstacle = layer_ptr(m, "obstacle");
-  cp.touched_keys = m->d_touched_keys;
-  launch_commit(cp, st_in, st_out, mp->d_counters, layer_table(m), s, m->lc);
 
-  const int bits = key_bits(m->cells);  // keys are in [0, cells]; `cells` = dropped point
-  FDEM_CUDA_TRY(sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_keys, mp->d_skeys,
-                               mp->d_vals, mp->d_svals, n, bits, s, m->lc));
-
-  EstimateParams ep{};
+  ScanLaunch& L = mp->launch;
+  L.pp = pp;
+  L.cp = CommitParams{};
+  L.cp.robot_x = in.robot_x;
+  L.cp.robot_y = in.robot_y;
+  L.cp.local_mode = pp.local_mode;
+  L.cp.clear_policy = cfg.move_clear_policy;
+  L.cp.invalid_key = pp.invalid_key;
+  L.cp.obstacle = layer_ptr(m, "obstacle");
+  L.cp.touched_keys = m->d_touched_keys;
+  L.cp.tile_path = tile ? 1 : 0;
+  L.cp.tb = mp->tb;
+  L.sp = ScatterParams{};
+  L.sp.keys = mp->d_keys;
+  L.sp.pm = mp->d_pm;
+  L.sp.intensity = inten_d;
+  L.sp.n = n;
+  L.sp.invalid_key = pp.invalid_key;
+  L.sp.tb = mp->tb;
+  L.sp.counters = mp->d_counters;
+  L.sp.st_cur = m->d_state;
+  L.sp.obstacle = L.cp.obstacle;
+  L.sp.touched_keys = m->d_touched_keys;
+  EstimateParams& ep = L.ep;
+  ep = EstimateParams{};
   ep.sorted_keys = mp->d_skeys;
   ep.sorted_vals = mp->d_svals;
   ep.pm = mp->d_pm;
@@ -506,42 +607,168 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
     ep.p2_max_sample_count = std::max(cfg.p2_max_sample_count, 0.0f);
   }
   ep.L = est_layers(m);
-  launch_segreduce_estimate(ep, mp->d_counters, mp->d_counters, s, m->lc);
-  FDEM_CUDA_TRY(cudaGetLastError());
+  L.lt = layer_table(m);
+  L.tb = mp->tb;
+  L.st_cur = m->d_state;
+  L.st_next = m->d_state + 1;
+  L.counters = mp->d_counters;
+  L.pm = mp->d_pm;
+  L.keys = mp->d_keys;
+  L.vals = mp->d_vals;
+  L.host_out = m->d_result_host;
 
-  m->parity ^= 1;
-  m->geom_stale = true;
-
-  if (cfg.raycasting_enabled && in.input_frame == INPUT_SENSOR_FRAME) {
-    // fastdem.cpp:153-159: sensor origin = (T_world_base*T_base_sensor).translation(),
-    // ray_scan = voxelGrid(points, resolution, ANY)
-    const float origin[3] = {static_cast<float>(T[12]), static_cast<float>(T[13]),
-                             static_cast<float>(T[14])};
-    const float voxel = static_cast<float>(m->geom.res);
-    if (voxel < 0.001f || voxel > 100.0f)
-      return set_error(FDEM_ERR_INVALID_ARGUMENT, "voxel_size must be in [0.001, 100]");
-    launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vals, s, m->lc);
-    FDEM_CUDA_TRY(sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys, mp->d_svkeys,
-                                 mp->d_vals, mp->d_svals, n, 64, s, m->lc));
-    launch_voxel_select(mp->d_svkeys, mp->d_svals, n, mp->d_counters, mp->d_sel, s, m->lc);
-    FDEM_TRY(raycast_device(m, cfg, origin, mp->d_pm, mp->d_sel, mp->d_counters + CNT_VOXELS, n,
-                            mp->d_counters));
+  const bool raycast = cfg.raycasting_enabled && in.input_frame == INPUT_SENSOR_FRAME;
+  // K3t's last CTA ends the scan itself unless more kernels follow (raycasting)
+  L.pub = PublishArgs{};
+  L.pub.enabled = (tile && !raycast) ? 1 : 0;
+  L.pub.st_cur = m->d_state;
+  L.pub.host_out = m->d_result_host;
+  const bool graph = tile && mp->use_graph && !mp->stage_timing && !raycast;
+  fdem_status launch_status = FDEM_OK;
+  if (graph) {
+    // K1 -> K2 -> scatter -> K3t -> publish as one cudaGraphLaunch; only the nodes whose
+    // arguments changed since the last scan are patched
+    launch_status = launch_scan_graph(mp, s);
+    m->lc.mine += GN_COUNT;
+  } else {
+    mark(FDEM_STAGE_PREPROCESS);
+    launch_preprocess_bin(pp, st_in, mp->d_counters, mp->d_pm, mp->d_keys, mp->d_vals, s, m->lc);
+    mark(FDEM_STAGE_COMMIT);
+    launch_commit(L.cp, st_in, st_out, mp->d_counters, L.lt, s, m->lc);
+    mark(FDEM_STAGE_SORT);
+    if (tile) {
+      // L1 of the 2-level sort: one scatter pass into the bucket segments K2 allocated
+      launch_scatter_records(L.sp, s, m->lc);
+    } else {
+      const int bits = key_bits(m->cells);  // keys are in [0, cells]; `cells` = dropped point
+      FDEM_CUDA_TRY(sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_keys, mp->d_skeys,
+                                   mp->d_vals, mp->d_svals, n, bits, s, m->lc));
+    }
+    mark(FDEM_STAGE_ESTIMATE);
+    if (tile) launch_tile_estimate(ep, mp->tb, mp->d_counters, st_out, L.pub, s, m->lc);
+    else launch_segreduce_estimate(ep, mp->d_counters, mp->d_counters, s, m->lc);
+    mark(FDEM_STAGE_RAYCAST);
+    if (raycast) {
+      // fastdem.cpp:153-159: sensor origin = (T_world_base*T_base_sensor).translation(),
+      // ray_scan = voxelGrid(points, resolution, ANY)
+      const float origin[3] = {static_cast<float>(T[12]), static_cast<float>(T[13]),
+                               static_cast<float>(T[14])};
+      const float voxel = static_cast<float>(m->geom.res);
+      if (voxel < 0.001f || voxel > 100.0f) {
+        launch_status = set_error(FDEM_ERR_INVALID_ARGUMENT, "voxel_size must be in [0.001, 100]");
+      } else {
+        launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vals, s, m->lc);
+        cudaError_t se = sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys,
+                                        mp->d_svkeys, mp->d_vals, mp->d_svals, n, 64, s, m->lc);
+        if (se != cudaSuccess) launch_status = set_error(FDEM_ERR_CUDA, cudaGetErrorString(se));
+        launch_voxel_select(mp->d_svkeys, mp->d_svals, n, mp->d_counters, mp->d_sel, s, m->lc);
+        if (launch_status == FDEM_OK)
+          launch_status = raycast_device(m, cfg, origin, mp->d_pm, mp->d_sel, st_out, n, mp->d_counters);
+      }
+    }
+    mark(FDEM_STAGE_COUNT);
+    // counters + committed state -> host (mapped pinned memory), state made current, counters re-armed
+    if (!L.pub.enabled)
+      launch_publish(mp->d_counters, m->d_state, m->d_state + 1, m->d_result_host, s, m->lc);
   }
-
-  // leave the scan's counters + committed state where the host can pick them up
-  FDEM_CUDA_TRY(cudaMemcpyAsync(m->h_result->counters, mp->d_counters,
-                                CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  FDEM_CUDA_TRY(cudaMemcpyAsync(&m->h_result->state, m->d_state + m->parity, sizeof(DeviceState),
-                                cudaMemcpyDeviceToHost, s));
+  {
+    cudaError_t le = cudaGetLastError();
+    if (launch_status == FDEM_OK && le != cudaSuccess)
+      launch_status = set_error(FDEM_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
+    if (launch_status != FDEM_OK) {
+      mp->tile_dirty = true;
+      mp->counters_dirty = true;
+      return launch_status;
+    }
+  }
+  m->geom_stale = true;
   mp->last_n = n;
   mp->last_had_work = true;
   mp->pending = true;
   return FDEM_OK;
 }
 
+// ── CUDA graph of one scan (tile path): explicit kernel nodes, patched in place ─────────
+struct NodeArgs {
+  KernelDesc d;
+  void* args[8];
+};
+
+void scan_node_args(ScanLaunch& L, uint32_t n, NodeArgs out[GN_COUNT]) {
+  out[GN_K1].d = desc_preprocess_bin(n);
+  out[GN_K1].args[0] = &L.pp; out[GN_K1].args[1] = &L.st_cur; out[GN_K1].args[2] = &L.counters;
+  out[GN_K1].args[3] = &L.pm; out[GN_K1].args[4] = &L.keys; out[GN_K1].args[5] = &L.vals;
+  out[GN_K2].d = desc_commit();
+  out[GN_K2].args[0] = &L.cp; out[GN_K2].args[1] = &L.st_cur; out[GN_K2].args[2] = &L.st_next;
+  out[GN_K2].args[3] = &L.counters; out[GN_K2].args[4] = &L.lt;
+  out[GN_SCATTER].d = desc_scatter_records(n);
+  out[GN_SCATTER].args[0] = &L.sp;
+  out[GN_K3T].d = desc_tile_estimate(L.tb.n_buckets);
+  out[GN_K3T].args[0] = &L.ep; out[GN_K3T].args[1] = &L.tb; out[GN_K3T].args[2] = &L.counters;
+  out[GN_K3T].args[3] = &L.st_next; out[GN_K3T].args[4] = &L.pub;
+}
+
+cudaKernelNodeParams node_params(NodeArgs& a) {
+  cudaKernelNodeParams kp{};
+  kp.func = const_cast<void*>(a.d.func);
+  kp.gridDim = a.d.grid;
+  kp.blockDim = a.d.block;
+  kp.sharedMemBytes = static_cast<unsigned int>(a.d.smem);
+  kp.kernelParams = a.args;
+  kp.extra = nullptr;
+  return kp;
+}
+
+void destroy_scan_graph(fdem_mapper* mp) {
+  if (mp->sg.exec) cudaGraphExecDestroy(mp->sg.exec);
+  if (mp->sg.graph) cudaGraphDestroy(mp->sg.graph);
+  mp->sg = ScanGraph{};
+}
+
+fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
+  ScanLaunch& L = mp->launch;
+  ScanGraph& G = mp->sg;
+  NodeArgs na[GN_COUNT];
+  scan_node_args(L, L.pp.n, na);
+  if (!G.valid) {
+    destroy_scan_graph(mp);
+    FDEM_CUDA_TRY(cudaGraphCreate(&G.graph, 0));
+    for (int i = 0; i < GN_COUNT; ++i) {
+      cudaKernelNodeParams kp = node_params(na[i]);
+      FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i], G.graph, i ? &G.node[i - 1] : nullptr,
+                                           i ? 1 : 0, &kp));
+    }
+    FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
+    G.cached = L;
+    G.valid = true;
+  } else {
+    const ScanLaunch& C = G.cached;
+    const bool shared_changed = L.st_cur != C.st_cur || L.st_next != C.st_next ||
+                                L.counters != C.counters || L.pm != C.pm || L.keys != C.keys ||
+                                L.vals != C.vals || L.host_out != C.host_out ||
+                                std::memcmp(&L.tb, &C.tb, sizeof(TileBuffers)) != 0;
+    bool dirty[GN_COUNT];
+    dirty[GN_K1] = shared_changed || std::memcmp(&L.pp, &C.pp, sizeof(L.pp)) != 0;
+    dirty[GN_K2] = shared_changed || std::memcmp(&L.cp, &C.cp, sizeof(L.cp)) != 0 ||
+                   std::memcmp(&L.lt, &C.lt, sizeof(L.lt)) != 0;
+    dirty[GN_SCATTER] = shared_changed || std::memcmp(&L.sp, &C.sp, sizeof(L.sp)) != 0;
+    dirty[GN_K3T] = shared_changed || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0 ||
+                    std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
+    for (int i = 0; i < GN_COUNT; ++i) {
+      if (!dirty[i]) continue;
+      cudaKernelNodeParams kp = node_params(na[i]);
+      FDEM_CUDA_TRY(cudaGraphExecKernelNodeSetParams(G.exec, G.node[i], &kp));
+    }
+    G.cached = L;
+  }
+  FDEM_CUDA_TRY(cudaGraphLaunch(G.exec, s));
+  return FDEM_OK;
+}
+
 fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
   fdem_map* m = mp->map;
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (!mp->ev_scans.empty()) drain_stage_events(mp);
   if (mp->last_had_work) {
     const ScanResult& r = *m->h_result;
     m->geom = r.state.geom;
@@ -663,8 +890,9 @@ fdem_status fdem_map_create_stripe(float width, float height, float resolution, 
   FDEM_CUDA_TRY(cudaMalloc(&m->d_state, 2 * sizeof(DeviceState)));
   FDEM_CUDA_TRY(cudaMemset(m->d_state, 0, 2 * sizeof(DeviceState)));
   FDEM_CUDA_TRY(cudaMalloc(&m->d_flag, 4 * sizeof(uint32_t)));
-  FDEM_CUDA_TRY(cudaHostAlloc(&m->h_result, sizeof(ScanResult), cudaHostAllocDefault));
+  FDEM_CUDA_TRY(cudaHostAlloc(&m->h_result, sizeof(ScanResult), cudaHostAllocMapped));
   std::memset(m->h_result, 0, sizeof(ScanResult));
+  FDEM_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->d_result_host), m->h_result, 0));
   fdem_status st = push_state(m, 0);
   if (st != FDEM_OK) return st;
   // ElevationMap() basic layers (elevation_map.hpp:99-103), then clearAll()
@@ -720,7 +948,7 @@ fdem_status fdem_map_get_geometry(fdem_map* m, fdem_geometry* out) {
 static fdem_status current_touched_count(fdem_map* m, uint32_t* out) {
   DeviceState st;
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
-  FDEM_CUDA_TRY(cudaMemcpy(&st, m->d_state + m->parity, sizeof(st), cudaMemcpyDeviceToHost));
+  FDEM_CUDA_TRY(cudaMemcpy(&st, m->d_state, sizeof(st), cudaMemcpyDeviceToHost));
   *out = st.touched_count;
   return FDEM_OK;
 }
@@ -757,10 +985,11 @@ fdem_status fdem_map_move(fdem_map* m, double x, double y, int32_t clear_policy,
   DeviceGuard dg(m->device);
   FDEM_REQUIRE(m->geom.row_begin == 0 && m->geom.row_end == m->geom.rows,
                "move() is not valid on a row stripe");
-  launch_move_only(m->d_state + m->parity, m->d_state + (m->parity ^ 1), x, y, clear_policy,
-                   layer_table(m), m->d_flag, m->stream, m->lc);
+  launch_move_only(m->d_state, m->d_state + 1, x, y, clear_policy, layer_table(m), m->d_flag,
+                   m->stream, m->lc);
   FDEM_CUDA_TRY(cudaGetLastError());
-  m->parity ^= 1;
+  FDEM_CUDA_TRY(cudaMemcpyAsync(m->d_state, m->d_state + 1, sizeof(DeviceState),
+                                cudaMemcpyDeviceToDevice, m->stream));
   m->geom_stale = true;
   FDEM_TRY(refresh_geometry(m));
   uint32_t flag = 0;
@@ -956,6 +1185,24 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
   if (st != FDEM_OK) { delete mp; return st; }
   cudaError_t e = cudaMalloc(&mp->d_counters, CNT_COUNT * sizeof(uint32_t));
   if (e != cudaSuccess) { delete mp; return set_error(FDEM_ERR_CUDA, cudaGetErrorString(e)); }
+  {
+    // tile path scratch: one counter / offset / cursor / list slot per 1024-cell bucket
+    const char* env = std::getenv("FDEM_CELL_SORT");
+    mp->use_tile = !(env && std::string(env) == "cub");
+    const char* genv = std::getenv("FDEM_GRAPH");
+    mp->use_graph = !(genv && std::string(genv) == "0");
+    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + kBucketCells - 1) >> kBucketBits);
+    const size_t nb = std::max<size_t>(mp->tb.n_buckets, 1) * sizeof(uint32_t);
+    cudaError_t e2 = cudaMalloc(&mp->tb.bucket_count, nb);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_offset, nb);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_cursor, nb);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_list, nb * 4);
+    if (e2 == cudaSuccess) e2 = static_cast<cudaError_t>(tile_estimate_configure());
+    if (e2 != cudaSuccess) {
+      fdem_mapper_destroy(mp);
+      return set_error(FDEM_ERR_CUDA, std::string("tile path setup failed: ") + cudaGetErrorString(e2));
+    }
+  }
   *out = mp;
   return FDEM_OK;
 }
@@ -965,7 +1212,14 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   DeviceGuard dg(mp->map->device);
   cudaStreamSynchronize(mp->map->stream);
   free_scratch(mp);
+  destroy_scan_graph(mp);
   cudaFree(mp->d_counters);
+  cudaFree(mp->tb.bucket_count);
+  cudaFree(mp->tb.bucket_offset);
+  cudaFree(mp->tb.bucket_cursor);
+  cudaFree(mp->tb.bucket_list);
+  drain_stage_events(mp);
+  for (cudaEvent_t e : mp->ev_pool) cudaEventDestroy(e);
   delete mp;
   return FDEM_OK;
 }
@@ -1130,6 +1384,47 @@ fdem_status fdem_mapper_last_rasterized(fdem_mapper* mp, float* xyz, int64_t* n_
     ++k;
   }
   *n_cells = k;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_set_cell_sort(fdem_mapper* mp, int32_t mode) {
+  FDEM_REQUIRE(mp, "null mapper");
+  FDEM_REQUIRE(mode == FDEM_CELL_SORT_TILE || mode == FDEM_CELL_SORT_GLOBAL, "bad cell sort mode");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  mp->use_tile = mode == FDEM_CELL_SORT_TILE;
+  mp->tile_dirty = true;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_set_stage_timing(fdem_mapper* mp, int32_t enabled) {
+  FDEM_REQUIRE(mp, "null mapper");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  drain_stage_events(mp);
+  mp->stage_timing = enabled != 0;
+  for (double& v : mp->stage_ms) v = 0.0;
+  mp->stage_scans = 0;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_stage_times(fdem_mapper* mp, double* ms, int64_t* scans) {
+  FDEM_REQUIRE(mp && ms && scans, "null argument");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  drain_stage_events(mp);
+  for (int i = 0; i < FDEM_STAGE_COUNT; ++i) {
+    ms[i] = mp->stage_ms[i];
+    mp->stage_ms[i] = 0.0;
+  }
+  *scans = mp->stage_scans;
+  mp->stage_scans = 0;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_library_launch_count(fdem_mapper* mp, int64_t* launches) {
+  FDEM_REQUIRE(mp && launches, "null argument");
+  *launches = mp->map->lc.library;
   return FDEM_OK;
 }
 

@@ -17,7 +17,36 @@ enum Counter : int {
   CNT_VOXELS = 3,    // voxelGrid(ANY) representatives
   CNT_RAYS = 4,      // rays traced
   CNT_RC_SKIP = 5,   // 1 when raycasting preconditions failed (sensor outside map)
-  CNT_COUNT = 8
+  CNT_REC_SLOTS = 8,   // tile path: record slots handed out to bucket segments
+  CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
+  CNT_WORK = 10,       // tile path: K3t's dynamic work counter
+  CNT_COUNT = 12
+};
+
+// ── tile path: 2-level sort-by-cell ───────────────────────────────────────────
+// L1 = radix partition of the scan into buckets of 2^kBucketBits consecutive cell keys
+// (global, one pass: histogram in K1, segment allocation in K2, scatter kernel);
+// L2 = per-bucket sort + warp-segmented reduce in shared memory (K3t).
+constexpr int kBucketBits = 10;
+constexpr uint32_t kBucketCells = 1u << kBucketBits;
+
+// one run of same-cell points, pre-reduced by the scatter kernel (fields = CellObs)
+struct alignas(32) CellRecord {
+  uint32_t lkey;  // cell index inside its bucket
+  float mz, mv;
+  uint32_t mi;
+  float xz, it;
+  uint32_t fi, li;
+};
+static_assert(sizeof(CellRecord) == 32, "CellRecord must be 32 bytes (TMA bulk-copy unit)");
+
+struct TileBuffers {
+  uint32_t* bucket_count;   // [n_buckets] points per bucket (K1); K3t re-zeroes what it consumed
+  uint32_t* bucket_offset;  // [n_buckets] first record slot of the bucket's segment (K2)
+  uint32_t* bucket_cursor;  // [n_buckets] records written so far (scatter); K3t re-zeroes
+  uint4* bucket_list;       // [n_buckets] non-empty buckets: {bucket, first slot, points, 0} (K2)
+  CellRecord* records;      // [capacity in points]
+  uint32_t n_buckets;
 };
 
 // State that survives from scan to scan and is decided on the device (so a stream of
@@ -53,6 +82,8 @@ struct PreprocessParams {
   float constant_variance;  // uncertainty^2
   int32_t local_mode;
   uint32_t invalid_key;  // = number of cells in this handle's slab
+  uint32_t* bucket_count;  // tile path: per-bucket point histogram (null on the global-sort path)
+  int32_t write_vals;      // global-sort path needs vals[i] = i
 };
 
 // pointers to every layer the estimator kernel reads or writes (null when absent)
@@ -97,6 +128,30 @@ struct CommitParams {
   uint32_t invalid_key;
   float* obstacle;
   const uint32_t* touched_keys;
+  int32_t tile_path;  // 1: also hand out bucket segments (TileBuffers) and let K3t count cells
+  TileBuffers tb;
+};
+
+struct ScatterParams {
+  const uint32_t* keys;
+  const float4* pm;
+  const float* intensity;
+  uint32_t n;
+  uint32_t invalid_key;
+  TileBuffers tb;
+  // the scatter grid also resets the last observing scan's obstacle cells (tile path)
+  const uint32_t* counters;
+  const DeviceState* st_cur;
+  float* obstacle;
+  const uint32_t* touched_keys;
+};
+
+// what K3t's last CTA needs to end the scan (publish); all null/0 when a separate
+// publish_kernel launch follows instead (raycasting enabled)
+struct PublishArgs {
+  DeviceState* st_cur;
+  uint32_t* host_out;
+  int32_t enabled;
 };
 
 struct RaycastParams {
@@ -126,10 +181,29 @@ void launch_preprocess_bin(const PreprocessParams& p, const DeviceState* st_in, 
                            float4* pm, uint32_t* keys, uint32_t* vals, cudaStream_t s,
                            LaunchCounter& lc);
 void launch_commit(const CommitParams& p, const DeviceState* st_in, DeviceState* st_out,
-                   const uint32_t* counters, const LayerTable& lt, cudaStream_t s,
-                   LaunchCounter& lc);
+                   uint32_t* counters, const LayerTable& lt, cudaStream_t s, LaunchCounter& lc);
 void launch_segreduce_estimate(const EstimateParams& p, const uint32_t* counters_ro,
                                uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+// host_out: CNT_COUNT counter words followed by the words of DeviceState (mapped pinned memory)
+void launch_publish(uint32_t* counters, DeviceState* st_cur, const DeviceState* st_next,
+                    uint32_t* host_out, cudaStream_t s, LaunchCounter& lc);
+// kernel entry + launch shape, for cudaGraphAddKernelNode / cudaLaunchKernel in capi.cu
+struct KernelDesc {
+  const void* func;
+  dim3 grid, block;
+  size_t smem;
+};
+KernelDesc desc_preprocess_bin(uint32_t n);
+KernelDesc desc_commit();
+KernelDesc desc_publish();
+KernelDesc desc_scatter_records(uint32_t n);
+KernelDesc desc_tile_estimate(uint32_t n_buckets);
+// tile path (kernels_tile.cu)
+void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc);
+void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
+                          DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
+                          LaunchCounter& lc);
+int tile_estimate_configure();  // one-time cudaFuncSetAttribute (dynamic smem); returns cudaError_t
 void launch_move_only(const DeviceState* st_in, DeviceState* st_out, double x, double y,
                       int clear_policy, const LayerTable& lt, uint32_t* moved_flag, cudaStream_t s,
                       LaunchCounter& lc);

@@ -2,12 +2,13 @@
 //
 //   K1 preprocess_bin_kernel      sensor covariance + SE(3) x2 + range/height crop +
 //                                 sigma_z^2 = (R S R^T)(2,2) + FP64 (x,y) -> cell key
+//                                 (+ per-bucket point histogram on the tile path)
 //   K2 commit_move_clear_kernel   LOCAL-mode circular-buffer move (vacated stripes -> NaN),
 //                                 reset of last scan's obstacle cells, scan-state commit
-//   (sort by cell: sort.cu)
-//   K3 segreduce_estimate_kernel  warp-segmented min/max reduce over the sorted stream +
-//                                 one Kalman / P2 state step per touched cell, every layer
-//                                 written once, no global atomics on estimator state
+//                                 (+ bucket segment allocation on the tile path)
+//   K3 segreduce_estimate_kernel  global-sort path: warp-segmented reduce over the
+//                                 CUB-sorted stream + one Kalman / P2 step per touched cell
+//   (tile path: kernels_tile.cu;  global sort: sort.cu)
 //
 // Compiled with -fmad=false: every float/double expression below is evaluated exactly as
 // written (no FMA contraction), in the operation order the CPU oracle fixes, so cell
@@ -17,14 +18,13 @@
 #include <math.h>
 
 #include "device_types.h"
+#include "estimator.cuh"
 
 namespace fdem {
 
 namespace {
 
 constexpr int kBlock = 256;
-
-__device__ __forceinline__ float nanf_() { return __int_as_float(0x7fc00000); }
 
 // ───────────────────────────── utility kernels ───────────────────────────────
 
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kBlock) any_not_nan_kernel(const float* __rest
 // ElevationMap::clearAt (elevation_map.hpp:131-135)
 __global__ void clear_cell_kernel(LayerTable lt, int64_t lin) {
   const int l = threadIdx.x;
-  if (l < lt.count) lt.ptr[l][lin] = nanf_();
+  if (l < lt.count) lt.ptr[l][lin] = nan_f32();
 }
 
 // ───────────────────────────── K1: preprocess + bin ──────────────────────────
@@ -137,6 +137,11 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   // so binning against the prospective geometry is always right.
   __shared__ GridGeom sg;
   __shared__ uint32_t s_kept, s_inside;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  // the point load does not depend on the geometry: put it in flight first
+  float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (i < p.n) q = __ldg(&p.xyzw[i]);
   if (threadIdx.x == 0) {
     GridGeom g = st_in->geom;
     if (p.local_mode) {
@@ -149,10 +154,9 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   }
   __syncthreads();
 
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool kept = false, inside = false;
+  uint32_t key = p.invalid_key;
   if (i < p.n) {
-    float4 q = __ldg(&p.xyzw[i]);
     float var_z = 0.0f;
     if (p.input_frame == INPUT_SENSOR_FRAME) {
       // preprocessScan (fastdem/src/fastdem.cpp:164-190)
@@ -177,7 +181,6 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
       if (p.var_z) var_z = __ldg(&p.var_z[i]);
     }
 
-    uint32_t key = p.invalid_key;
     if (kept) {
       int32_t row, col;
       if (geom_get_index(sg, static_cast<double>(q.x), static_cast<double>(q.y), row, col)) {
@@ -189,18 +192,27 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
       }
       pm[i] = make_float4(q.x, q.y, q.z, var_z);
     } else {
-      pm[i] = make_float4(nanf_(), nanf_(), nanf_(), 0.0f);  // dropped by the crop filters
+      pm[i] = make_float4(nan_f32(), nan_f32(), nan_f32(), 0.0f);  // dropped by the crop filters
     }
     keys[i] = key;
-    vals[i] = i;
+    if (p.write_vals) vals[i] = i;
   }
 
-  // block-level counts -> one atomic per block per counter (scan statistics, not map state)
-  const uint32_t kept_w = __popc(__ballot_sync(0xffffffffu, kept));
-  const uint32_t inside_w = __popc(__ballot_sync(0xffffffffu, inside));
-  if ((threadIdx.x & 31) == 0) {
-    if (kept_w) atomicAdd(&s_kept, kept_w);
-    if (inside_w) atomicAdd(&s_inside, inside_w);
+  const uint32_t kept_m = __ballot_sync(0xffffffffu, kept);
+  const uint32_t inside_m = __ballot_sync(0xffffffffu, inside);
+
+  // tile path, L1 histogram: points per bucket of 2^kBucketBits consecutive cell keys.
+  // One atomic per (warp, bucket) — scan-sized scratch, never map state.
+  if (p.bucket_count && inside) {
+    const uint32_t bucket = key >> kBucketBits;
+    const uint32_t peers = __match_any_sync(inside_m, bucket);
+    if (lane == __ffs(peers) - 1) atomicAdd(&p.bucket_count[bucket], __popc(peers));
+  }
+
+  // block-level counts -> one atomic per block per counter (scan statistics)
+  if (lane == 0) {
+    if (kept_m) atomicAdd(&s_kept, __popc(kept_m));
+    if (inside_m) atomicAdd(&s_inside, __popc(inside_m));
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -220,7 +232,7 @@ __device__ __forceinline__ void clear_spans(const GridGeom& g, const MoveResult&
   for (int li = 0; li < n_layers; ++li) {
     float* __restrict__ d = lt.ptr[(policy == 1) ? lt.basic[li] : li];
     if (mr.clear_all) {
-      for (size_t c = tid; c < cells; c += nthreads) d[c] = nanf_();
+      for (size_t c = tid; c < cells; c += nthreads) d[c] = nan_f32();
       continue;
     }
     for (int sidx = 0; sidx < mr.n_spans; ++sidx) {
@@ -230,12 +242,12 @@ __device__ __forceinline__ void clear_spans(const GridGeom& g, const MoveResult&
         for (size_t t = tid; t < total; t += nthreads) {
           const size_t c = t / sp.n;
           const size_t r = sp.k + (t - c * sp.n);
-          d[c * rows_local + r] = nanf_();
+          d[c * rows_local + r] = nan_f32();
         }
       } else {  // buffer columns [k, k+n): contiguous in column-major storage
         const size_t total = static_cast<size_t>(sp.n) * rows_local;
         float* __restrict__ base = d + static_cast<size_t>(sp.k) * rows_local;
-        for (size_t t = tid; t < total; t += nthreads) base[t] = nanf_();
+        for (size_t t = tid; t < total; t += nthreads) base[t] = nan_f32();
       }
     }
   }
@@ -244,42 +256,116 @@ __device__ __forceinline__ void clear_spans(const GridGeom& g, const MoveResult&
 __global__ void __launch_bounds__(kBlock)
 commit_move_clear_kernel(const __grid_constant__ CommitParams p,
                          const DeviceState* __restrict__ st_in, DeviceState* __restrict__ st_out,
-                         const uint32_t* __restrict__ counters,
+                         uint32_t* __restrict__ counters,
                          const __grid_constant__ LayerTable lt) {
+  // The three jobs of this kernel are independent, so the grid is split into role groups
+  // that run them side by side (each job is a short chain of dependent memory round trips;
+  // doing them one after another in every thread would add the chains up):
+  //   group A  bucket segment allocation (tile path)
+  //   group B  reset of the last observing scan's obstacle cells
+  //   group C  state commit + circular-buffer move (vacated rows / columns -> NaN)
+  const int lane = threadIdx.x & 31;
+  const uint32_t nA = p.tile_path ? gridDim.x / 2 : 0;
+  const uint32_t nB = p.tile_path ? 0 : gridDim.x / 2;  // tile path: the scatter grid does job B
+  const uint32_t s_inside = counters[CNT_INSIDE];
+
+  if (blockIdx.x < nA) {
+    // tile path, L1 segment allocation: every non-empty bucket gets a contiguous run of
+    // record slots sized by its point count (an upper bound on its records) and joins the
+    // work list.  Where a bucket lands is irrelevant to the result, so no global prefix
+    // scan is needed — two atomics per WARP of 32 buckets, on scan scratch.
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nthreads = static_cast<size_t>(nA) * blockDim.x;
+    for (size_t b = tid; b - lane < p.tb.n_buckets; b += nthreads) {
+      const uint32_t cnt = b < p.tb.n_buckets ? p.tb.bucket_count[b] : 0u;
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t nz = __ballot_sync(0xffffffffu, cnt != 0);
+      uint32_t slot0 = 0, list0 = 0;
+      if (lane == 0 && total) {
+        slot0 = atomicAdd(&counters[CNT_REC_SLOTS], total);
+        list0 = atomicAdd(&counters[CNT_BUCKETS], __popc(nz));
+      }
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      list0 = __shfl_sync(0xffffffffu, list0, 0);
+      if (cnt) {
+        const uint32_t off = slot0 + incl - cnt;
+        p.tb.bucket_offset[b] = off;
+        p.tb.bucket_list[list0 + __popc(nz & ((1u << lane) - 1u))] =
+            make_uint4(static_cast<uint32_t>(b), off, cnt, 0u);
+      }
+    }
+    return;
+  }
+
+  if (blockIdx.x < nA + nB) {
+    // updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146) restricted to the
+    // cells that can hold a value: those the last observing scan touched.  Runs only when
+    // this scan has observations (update() returns early otherwise, :116-117).
+    if (s_inside > 0 && p.obstacle) {
+      const uint32_t prev = st_in->touched_count;
+      const size_t tid = static_cast<size_t>(blockIdx.x - nA) * blockDim.x + threadIdx.x;
+      const size_t nthreads = static_cast<size_t>(nB) * blockDim.x;
+      for (size_t j = tid; j < prev; j += nthreads) {
+        const uint32_t k = p.touched_keys[j];
+        if (k != p.invalid_key) p.obstacle[k] = nan_f32();
+      }
+    }
+    return;
+  }
+
   __shared__ GridGeom g_new;
   __shared__ MoveResult mr;
-  __shared__ uint32_t s_inside, s_prev_touched;
   if (threadIdx.x == 0) {
     const GridGeom g_old = st_in->geom;
     const uint32_t kept = counters[CNT_KEPT];
-    s_inside = counters[CNT_INSIDE];
-    s_prev_touched = st_in->touched_count;
     mr.moved = 0;
     mr.clear_all = 0;
     mr.n_spans = 0;
     g_new = g_old;
     // map_.move() runs only when preprocessScan left >= 1 point (fastdem.cpp:137-138)
     if (p.local_mode && kept > 0) g_new = geom_move(g_old, p.robot_x, p.robot_y, mr);
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == nA + nB) {
       st_out->geom = g_new;
-      // the touched list is replaced by K3 only when this scan produced observations
-      st_out->touched_count = s_inside > 0 ? s_inside : s_prev_touched;
+      // The touched list is replaced only when this scan produced observations.  Global
+      // sort path: K3 writes one slot per sorted element (invalid_key except at segment
+      // tails).  Tile path: K3t appends compactly and counts up from 0.
+      if (s_inside > 0) st_out->touched_count = p.tile_path ? 0u : s_inside;
+      else st_out->touched_count = st_in->touched_count;
     }
   }
   __syncthreads();
-  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (mr.clear_all || mr.n_spans > 0) {
+    const uint32_t nC = gridDim.x - nA - nB;
+    const size_t tid = static_cast<size_t>(blockIdx.x - nA - nB) * blockDim.x + threadIdx.x;
+    clear_spans(g_new, mr, lt, p.clear_policy, tid, static_cast<size_t>(nC) * blockDim.x);
+  }
+}
 
-  if (mr.clear_all || mr.n_spans > 0) clear_spans(g_new, mr, lt, p.clear_policy, tid, nthreads);
-
-  // updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146) restricted to the
-  // cells that can hold a value: those the last observing scan touched.  Runs only when
-  // this scan has observations (update() returns early otherwise, :116-117).
-  if (s_inside > 0 && p.obstacle) {
-    for (size_t j = tid; j < s_prev_touched; j += nthreads) {
-      const uint32_t k = p.touched_keys[j];
-      if (k != p.invalid_key) p.obstacle[k] = nanf_();
-    }
+// End of a scan: hand the scan statistics + committed state to the host (pinned, mapped
+// memory — no memcpy nodes), make the committed state current, and re-arm the counters for
+// the next scan (no memset node).  One warp.
+__global__ void publish_kernel(uint32_t* __restrict__ counters, DeviceState* __restrict__ st_cur,
+                               const DeviceState* __restrict__ st_next,
+                               uint32_t* __restrict__ host_out) {
+  constexpr int kStateWords = sizeof(DeviceState) / 4;
+  static_assert(sizeof(DeviceState) % 4 == 0 && kStateWords <= 32 && CNT_COUNT <= 32, "one warp");
+  const int t = threadIdx.x;
+  uint32_t c = 0, w = 0;
+  if (t < CNT_COUNT) c = counters[t];
+  if (t < kStateWords) w = reinterpret_cast<const uint32_t*>(st_next)[t];
+  if (t < CNT_COUNT) {
+    host_out[t] = c;
+    counters[t] = 0;
+  }
+  if (t < kStateWords) {
+    host_out[CNT_COUNT + t] = w;
+    reinterpret_cast<uint32_t*>(st_cur)[t] = w;
   }
 }
 
@@ -305,210 +391,10 @@ move_only_kernel(const DeviceState* __restrict__ st_in, DeviceState* __restrict_
 }
 
 // ───────────────────────────── K3: segmented reduce + estimator ──────────────
-
-// per-scan observation of one cell (ElevationMapping::CellObservation,
-// mapping/elevation_mapping.hpp:26-34) as carried through the segmented scan
-struct Obs {
-  float mz;  // min_z        (init FLT_MAX)
-  float mv;  // min_z_var    (variance of the FIRST point attaining min_z)
-  float xz;  // max_z        (init -FLT_MAX)
-  float it;  // max intensity over non-NaN values (init -inf)
-};
-
-// left-biased combine: `a` precedes `b` in point-index order (the sort is stable), so a
-// strict `<` keeps the lowest-index point on equal min_z — rasterize()'s `z < cell.min_z`
-// (elevation_mapping.cpp:65-68)
-__device__ __forceinline__ Obs combine(const Obs& a, const Obs& b) {
-  Obs r;
-  const bool take_b = b.mz < a.mz;
-  r.mz = take_b ? b.mz : a.mz;
-  r.mv = take_b ? b.mv : a.mv;
-  r.xz = (b.xz > a.xz) ? b.xz : a.xz;
-  r.it = (b.it > a.it) ? b.it : a.it;
-  return r;
-}
-
-__device__ __forceinline__ Obs shfl_up_obs(const Obs& v, int d) {
-  Obs r;
-  r.mz = __shfl_up_sync(0xffffffffu, v.mz, d);
-  r.mv = __shfl_up_sync(0xffffffffu, v.mv, d);
-  r.xz = __shfl_up_sync(0xffffffffu, v.xz, d);
-  r.it = __shfl_up_sync(0xffffffffu, v.it, d);
-  return r;
-}
-__device__ __forceinline__ Obs shfl_obs(const Obs& v, int src) {
-  Obs r;
-  r.mz = __shfl_sync(0xffffffffu, v.mz, src);
-  r.mv = __shfl_sync(0xffffffffu, v.mv, src);
-  r.xz = __shfl_sync(0xffffffffu, v.xz, src);
-  r.it = __shfl_sync(0xffffffffu, v.it, src);
-  return r;
-}
-
-// Kalman::update + computeBounds on one cell (mapping/kalman_estimation.hpp:98-153)
-__device__ __forceinline__ void kalman_cell(const EstimateParams& p, uint32_t c, float z,
-                                            float meas_var) {
-  const EstLayers& L = p.L;
-  float x = L.elevation[c];
-  float P = L.kalman_p[c];
-  float count = L.n_points[c];
-  float mean = L.sample_mean[c];
-  float svar = L.variance[c];
-  float m2 = L.sample_m2[c];
-
-  const float R = (meas_var > 0.0f) ? meas_var : p.kalman_max_variance;
-  if (isnan(x)) {
-    x = z;
-    P = R;
-    count = 1.0f;
-  } else {
-    P += p.kalman_process_noise;
-    const float K = P / (P + R);
-    x = x + K * (z - x);
-    P = (1.0f - K) * P;
-    P = fminf(fmaxf(P, p.kalman_min_variance), p.kalman_max_variance);
-    count += 1.0f;
-  }
-  if (isnan(mean)) {
-    mean = z;
-    svar = 0.0f;
-    m2 = 0.0f;
-  } else {
-    const float delta = z - mean;
-    const float new_mean = mean + (delta / count);
-    const float delta2 = z - new_mean;
-    m2 += delta * delta2;
-    svar = (count > 1.0f) ? m2 / (count - 1.0f) : 0.0f;
-    mean = new_mean;
-  }
-  const float sigma = sqrtf(fmaxf(0.0f, svar));
-  L.elevation[c] = x;
-  L.kalman_p[c] = P;
-  L.n_points[c] = count;
-  L.sample_mean[c] = mean;
-  L.variance[c] = svar;
-  L.sample_m2[c] = m2;
-  L.upper_bound[c] = x + 2.0f * sigma;
-  L.lower_bound[c] = x - 2.0f * sigma;
-}
-
-__device__ __forceinline__ float p2_parabolic(const float* q, const float* n, int i, int sign) {
-  const float d_right = n[i + 1] - n[i];
-  const float d_left = n[i] - n[i - 1];
-  const float d_span = n[i + 1] - n[i - 1];
-  if (d_right == 0.0f || d_left == 0.0f || d_span == 0.0f) return q[i];
-  const float s = static_cast<float>(sign);
-  const float t1 = (d_left + s) * (q[i + 1] - q[i]) / d_right;
-  const float t2 = (d_right - s) * (q[i] - q[i - 1]) / d_left;
-  return q[i] + s * (t1 + t2) / d_span;
-}
-__device__ __forceinline__ float p2_linear(const float* q, const float* n, int i, int sign) {
-  const int j = i + sign;
-  const float dn = n[j] - n[i];
-  if (dn == 0.0f) return q[i];
-  return q[i] + static_cast<float>(sign) * (q[j] - q[i]) / dn;
-}
-
-// P2Quantile::update + updateP2 + computeBounds on one cell
-// (mapping/quantile_estimation.hpp:141-258)
-__device__ __forceinline__ void p2_cell(const EstimateParams& p, uint32_t c, float x) {
-  const EstLayers& L = p.L;
-  float q[5], n[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    q[k] = L.p2_q[k][c];
-    n[k] = L.p2_n[k][c];
-  }
-  float count = L.n_points[c];
-  if (isnan(count) || count < 0.0f) count = 0.0f;
-  if (count < 5.0f) {
-    // phase 1: collect the first five samples
-    const int slot = static_cast<int>(count);
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (k == slot) q[k] = x;
-    count += 1.0f;
-    if (count >= 5.0f) {
-      // std::sort(q, q+5): insertion sort, as libstdc++ does below 16 elements
-#pragma unroll
-      for (int i = 1; i < 5; ++i) {
-        const float v = q[i];
-        int j = i - 1;
-        while (j >= 0 && v < q[j]) {
-          q[j + 1] = q[j];
-          --j;
-        }
-        q[j + 1] = v;
-      }
-#pragma unroll
-      for (int i = 0; i < 5; ++i) n[i] = static_cast<float>(i);
-    }
-  } else {
-    int k;
-    if (x < q[0]) {
-      q[0] = x;
-      k = 0;
-    } else if (x < q[1]) {
-      k = 0;
-    } else if (x < q[2]) {
-      k = 1;
-    } else if (x < q[3]) {
-      k = 2;
-    } else if (x <= q[4]) {
-      k = 3;
-    } else {
-      q[4] = x;
-      k = 3;
-    }
-#pragma unroll
-    for (int i = 1; i < 5; ++i)
-      if (i > k) n[i] += 1.0f;
-    float n_prime[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) n_prime[i] = p.p2_dn[i] * count;  // pre-increment count (:216-219)
-    count += 1.0f;
-    if (p.p2_max_sample_count > 0.0f && count > p.p2_max_sample_count) {
-      const float scale = p.p2_max_sample_count / count;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) n[i] *= scale;
-      count = p.p2_max_sample_count;
-    }
-#pragma unroll
-    for (int i = 1; i < 4; ++i) {
-      const float d = n_prime[i] - n[i];
-      if ((d >= 1.0f && n[i + 1] - n[i] > 1.0f) || (d <= -1.0f && n[i - 1] - n[i] < -1.0f)) {
-        const int sign = (d >= 0.0f) ? 1 : -1;
-        const float q_new = p2_parabolic(q, n, i, sign);
-        q[i] = (q[i - 1] < q_new && q_new < q[i + 1]) ? q_new : p2_linear(q, n, i, sign);
-        n[i] += static_cast<float>(sign);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    L.p2_q[k][c] = q[k];
-    L.p2_n[k][c] = n[k];
-  }
-  L.n_points[c] = count;
-  // update() writes (count>=5 ? q[m] : x) but computeBounds() immediately overwrites
-  // elevation with q[m] (:161-162, :172) — only the latter survives estimate().
-  float qm = q[0];
-#pragma unroll
-  for (int k = 1; k < 5; ++k)
-    if (k == p.p2_marker) qm = q[k];
-  L.elevation[c] = qm;
-  const float sigma = (q[3] - q[1]) / 2.0f;
-  L.variance[c] = sigma * sigma;
-  L.lower_bound[c] = q[0];
-  L.upper_bound[c] = q[4];
-}
-
-constexpr int kK3Windows = 4;                  // 32-element windows per warp chunk
-constexpr int kK3Chunk = 32 * kK3Windows;      // sorted elements whose segment HEADS a warp owns
-
-// One warp owns every segment (cell) whose first sorted element lies in its chunk; it
-// follows a segment past the chunk end if needed, 32 elements per step, so a cell is
-// always reduced and written by exactly one lane of exactly one warp.
+// Global-sort path.  One warp owns every segment (cell) whose first sorted element lies
+// in its 32-element window; it follows a segment past the window if needed, 32 elements
+// per step, so a cell is always reduced and written by exactly one lane of exactly one
+// warp.  Reduction = segmented inclusive scan over warp shuffles.
 __global__ void __launch_bounds__(kBlock)
 segreduce_estimate_kernel(const __grid_constant__ EstimateParams p,
                           const uint32_t* __restrict__ counters_ro,
@@ -516,24 +402,23 @@ segreduce_estimate_kernel(const __grid_constant__ EstimateParams p,
   const uint32_t n_valid = min(counters_ro[CNT_INSIDE], p.n_sorted);
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t chunk_begin64 = static_cast<uint64_t>(warp_global) * kK3Chunk;
+  const uint64_t chunk_begin64 = static_cast<uint64_t>(warp_global) * 32u;
   if (chunk_begin64 >= n_valid) return;
   const uint32_t chunk_begin = static_cast<uint32_t>(chunk_begin64);
-  const uint32_t chunk_end = min(chunk_begin + static_cast<uint32_t>(kK3Chunk), n_valid);
+  const uint32_t chunk_end = min(chunk_begin + 32u, n_valid);
   const uint32_t INV = p.invalid_key;
   const bool has_i = p.intensity != nullptr;
-  const bool has_c = p.rgb != nullptr;
 
   bool open = false;  // an owned segment is open at the start of the window (warp-uniform)
-  Obs carry;
-  carry.mz = FLT_MAX; carry.mv = 0.0f; carry.xz = -FLT_MAX; carry.it = -INFINITY;
-  bool carry_first_nan = false;
+  CellObs carry = obs_identity();
   uint32_t cells_done = 0;
 
   for (uint32_t base = chunk_begin;; base += 32) {
     const uint32_t i = base + lane;
     const bool valid = i < n_valid;
+    // keys and point indices are independent loads: issue both before anything depends on them
     const uint32_t k = valid ? __ldg(&p.sorted_keys[i]) : INV;
+    const uint32_t idx = valid ? __ldg(&p.sorted_vals[i]) : 0u;
     uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
     if (lane == 0) kprev = (i > 0 && valid) ? __ldg(&p.sorted_keys[i - 1]) : INV;
     uint32_t knext = __shfl_down_sync(0xffffffffu, k, 1);
@@ -547,36 +432,21 @@ segreduce_estimate_kernel(const __grid_constant__ EstimateParams p,
     const int s = head_in_win ? (31 - __clz(m)) : 0;          // lane where my segment starts
     const bool owned = valid && (head_in_win ? (base + s < chunk_end) : open);
 
-    Obs v;
-    v.mz = FLT_MAX; v.mv = 0.0f; v.xz = -FLT_MAX; v.it = -INFINITY;
-    bool my_nan = false;
-    uint32_t idx = 0;
+    CellObs v = obs_identity();
     if (owned) {
-      idx = __ldg(&p.sorted_vals[i]);
       const float4 q = __ldg(&p.pm[idx]);
-      // rasterize() folds from {FLT_MAX, 0, lowest}: a point only enters through a strict
-      // compare, so NaN / out-of-range z leave the initial values in place
-      if (q.z < FLT_MAX) { v.mz = q.z; v.mv = q.w; }
-      if (q.z > -FLT_MAX) v.xz = q.z;
-      if (has_i) {
-        const float in = __ldg(&p.intensity[idx]);
-        my_nan = isnan(in);
-        if (!my_nan) v.it = in;
-      }
+      const float in = has_i ? __ldg(&p.intensity[idx]) : 0.0f;
+      v = obs_from_point(q.z, q.w, in, has_i, idx);
     }
 
     // segmented inclusive scan within the window (Hillis-Steele over shuffles)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const Obs o = shfl_up_obs(v, d);
-      if (lane - d >= s) v = combine(o, v);
+      const CellObs o = obs_shfl_up(v, d);
+      if (lane - d >= s) v = obs_combine(o, v);
     }
-    bool first_nan = __shfl_sync(0xffffffffu, my_nan, s);
-    if (!head_in_win) {
-      // my segment started in an earlier window: fold the carried prefix in from the left
-      if (open) v = combine(carry, v);
-      first_nan = carry_first_nan;
-    }
+    // my segment started in an earlier window: fold the carried prefix in
+    if (!head_in_win && open) v = obs_combine(carry, v);
 
     // touched-cell list for the next scan's obstacle reset: the key sits at the segment's
     // TAIL position (where min_z is known), invalid_key everywhere else
@@ -584,32 +454,7 @@ segreduce_estimate_kernel(const __grid_constant__ EstimateParams p,
 
     if (owned && tail) {
       ++cells_done;
-      const uint32_t c = k;
-      // estimate(): estimator.update(idx, min_z, min_z_var) + computeBounds (elevation_mapping.cpp:94-108)
-      if (p.estimation_type == 1) p2_cell(p, c, v.mz);
-      else kalman_cell(p, c, v.mz, v.mv);
-      // updateMinMax (elevation_mapping.cpp:127-142)
-      const float smin = p.L.elevation_min[c];
-      if (isnan(smin) || v.mz < smin) p.L.elevation_min[c] = v.mz;
-      const float smax = p.L.elevation_max[c];
-      if (isnan(smax) || v.xz > smax) p.L.elevation_max[c] = v.xz;
-      // updateObstacle (elevation_mapping.cpp:144-152)
-      p.L.obstacle[c] = (v.xz > v.mz) ? v.xz : nanf_();
-      // updateIntensity (elevation_mapping.cpp:154-166): the per-scan max is NaN only when the
-      // first point of the cell carries NaN (rasterize :72-78 takes the first value blindly)
-      if (has_i) {
-        const float mi = first_nan ? nanf_() : v.it;
-        const float stored = p.L.intensity[c];
-        if (isnan(stored) || mi > stored) p.L.intensity[c] = mi;
-      }
-      // updateColor (elevation_mapping.cpp:168-175): last point of the cell wins; the tail
-      // lane IS the last point (stable sort).  0x00RRGGBB reinterpreted as float.
-      if (has_c) {
-        const uint8_t* rgb = p.rgb + static_cast<size_t>(idx) * 3;
-        const uint32_t bits = (static_cast<uint32_t>(rgb[0]) << 16) |
-                              (static_cast<uint32_t>(rgb[1]) << 8) | rgb[2];
-        reinterpret_cast<uint32_t*>(p.L.color)[c] = bits;
-      }
+      apply_observation(p, k, v);
       if (p.touched_minz) p.touched_minz[i] = v.mz;
     }
 
@@ -618,11 +463,8 @@ segreduce_estimate_kernel(const __grid_constant__ EstimateParams p,
     const int last_lane = remaining >= 32 ? 31 : static_cast<int>(remaining) - 1;
     const bool last_tail = __shfl_sync(0xffffffffu, tail, last_lane);
     const bool last_owned = __shfl_sync(0xffffffffu, owned, last_lane);
-    const Obs last_v = shfl_obs(v, last_lane);
-    const bool last_first_nan = __shfl_sync(0xffffffffu, first_nan, last_lane);
+    carry = obs_shfl(v, last_lane);
     open = last_owned && !last_tail;
-    carry = last_v;
-    carry_first_nan = last_first_nan;
     if (remaining <= 32) break;                     // stream exhausted
     if (base + 32 >= chunk_end && !open) break;     // nothing of mine continues
   }
@@ -673,15 +515,19 @@ void launch_preprocess_bin(const PreprocessParams& p, const DeviceState* st_in, 
   ++lc.mine;
 }
 void launch_commit(const CommitParams& p, const DeviceState* st_in, DeviceState* st_out,
-                   const uint32_t* counters, const LayerTable& lt, cudaStream_t s,
-                   LaunchCounter& lc) {
-  commit_move_clear_kernel<<<148 * 2, kBlock, 0, s>>>(p, st_in, st_out, counters, lt);
+                   uint32_t* counters, const LayerTable& lt, cudaStream_t s, LaunchCounter& lc) {
+  commit_move_clear_kernel<<<148, kBlock, 0, s>>>(p, st_in, st_out, counters, lt);
+  ++lc.mine;
+}
+void launch_publish(uint32_t* counters, DeviceState* st_cur, const DeviceState* st_next,
+                    uint32_t* host_out, cudaStream_t s, LaunchCounter& lc) {
+  publish_kernel<<<1, 32, 0, s>>>(counters, st_cur, st_next, host_out);
   ++lc.mine;
 }
 void launch_segreduce_estimate(const EstimateParams& p, const uint32_t* counters_ro,
                                uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
   if (p.n_sorted == 0) return;
-  const size_t warps = (static_cast<size_t>(p.n_sorted) + kK3Chunk - 1) / kK3Chunk;
+  const size_t warps = (static_cast<size_t>(p.n_sorted) + 31) / 32;
   const int grid = static_cast<int>((warps * 32 + kBlock - 1) / kBlock);
   segreduce_estimate_kernel<<<grid, kBlock, 0, s>>>(p, counters_ro, counters);
   ++lc.mine;
@@ -689,8 +535,23 @@ void launch_segreduce_estimate(const EstimateParams& p, const uint32_t* counters
 void launch_move_only(const DeviceState* st_in, DeviceState* st_out, double x, double y,
                       int clear_policy, const LayerTable& lt, uint32_t* moved_flag, cudaStream_t s,
                       LaunchCounter& lc) {
-  move_only_kernel<<<148 * 2, kBlock, 0, s>>>(st_in, st_out, x, y, clear_policy, lt, moved_flag);
+  move_only_kernel<<<148, kBlock, 0, s>>>(st_in, st_out, x, y, clear_policy, lt, moved_flag);
   ++lc.mine;
 }
 
+}  // namespace fdem
+
+// ── launch descriptors for the per-scan CUDA graph (capi.cu packs the arguments) ──
+namespace fdem {
+KernelDesc desc_preprocess_bin(uint32_t n) {
+  return KernelDesc{reinterpret_cast<const void*>(&preprocess_bin_kernel),
+                    dim3((n + kBlock - 1) / kBlock), dim3(kBlock), 0};
+}
+KernelDesc desc_commit() {
+  return KernelDesc{reinterpret_cast<const void*>(&commit_move_clear_kernel), dim3(148),
+                    dim3(kBlock), 0};
+}
+KernelDesc desc_publish() {
+  return KernelDesc{reinterpret_cast<const void*>(&publish_kernel), dim3(1), dim3(32), 0};
+}
 }  // namespace fdem

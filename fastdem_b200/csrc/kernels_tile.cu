@@ -1,0 +1,413 @@
+// kernels_tile.cu — the tile path: a 2-level sort-by-cell built for this workload.
+//
+// A scan's points land in a few hundred "buckets" of 1024 consecutive cell keys.  Instead
+// of a general radix sort of the whole scan (5 CUB launches, ~60 us at 131K points on
+// B200 — launch/latency bound), the scan is sorted hierarchically:
+//
+//   L1  radix partition by bucket, ONE global pass:
+//         K1   per-bucket point histogram (kernels.cu, fused into preprocess+bin)
+//         K2   segment allocation per non-empty bucket (kernels.cu, fused into commit)
+//         scatter_records_kernel: consecutive same-cell points of a warp are pre-reduced
+//              with a segmented shuffle scan (LiDAR rings / image rows are coherent), and
+//              one 32-byte CellRecord per run is written into its bucket's segment
+//   L2  tile_estimate_kernel, one CTA per non-empty bucket (dynamic work list):
+//         the bucket's records are staged into shared memory with TMA bulk copies
+//         (cp.async.bulk + mbarrier), counting-sorted by cell inside shared memory,
+//         reduced per cell with a warp-segmented shuffle scan, merged into per-cell
+//         accumulators, and finally thread t applies the Kalman / P2 step to cell
+//         (bucket base + t): layer loads and stores are fully coalesced and each touched
+//         cell of each layer is written exactly once, with plain stores.
+//
+// Atomics appear only on scan-sized scratch (bucket cursors, shared-memory bins, scan
+// statistics) — never on estimator state.  Results are independent of every ordering the
+// atomics leave open because CellObs::combine carries explicit point-index tie-breaks.
+#include <float.h>
+#include <math.h>
+
+#include "device_types.h"
+#include "estimator.cuh"
+
+namespace fdem {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 1024;  // records staged per bulk copy (32 KiB)
+constexpr uint32_t kNone = 0xffffffffu;
+
+// ── shared-memory / TMA plumbing (inline PTX; SASS: UBLKCP + SYNCS) ──────────────
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ CellObs obs_of(const CellRecord& r) {
+  CellObs o;
+  o.mz = r.mz; o.mv = r.mv; o.mi = r.mi; o.xz = r.xz; o.it = r.it; o.fi = r.fi; o.li = r.li;
+  return o;
+}
+
+// ───────────────────────────── L1: scatter into bucket segments ──────────────
+__global__ void __launch_bounds__(kThreads)
+scatter_records_kernel(const __grid_constant__ ScatterParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t INV = p.invalid_key;
+  uint32_t key = INV;
+  CellObs v = obs_identity();
+  // all loads of this thread are independent: issue them together
+  const uint32_t n_inside = p.counters[CNT_INSIDE];
+  const uint32_t n_prev = p.st_cur->touched_count;
+  if (i < p.n) {
+    key = __ldg(&p.keys[i]);
+    const float4 q = __ldg(&p.pm[i]);
+    const bool has_i = p.intensity != nullptr;
+    const float in = has_i ? __ldg(&p.intensity[i]) : 0.0f;
+    if (key != INV) v = obs_from_point(q.z, q.w, in, has_i, i);
+  }
+  // updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146) restricted to the cells
+  // that can hold a value: those the last observing scan touched.  Runs only when this scan
+  // has observations (update() returns early otherwise, :116-117); K3t writes this scan's
+  // values afterwards.
+  if (n_inside > 0 && p.obstacle) {
+    for (uint32_t j = i; j < n_prev; j += gridDim.x * blockDim.x) {
+      const uint32_t k = p.touched_keys[j];
+      if (k != INV) p.obstacle[k] = nan_f32();
+    }
+  }
+  // runs of consecutive lanes that hit the same cell
+  uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  uint32_t knext = __shfl_down_sync(0xffffffffu, key, 1);
+  const bool head = lane == 0 || key != kprev;
+  const bool tail = lane == 31 || key != knext;
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const int s = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // lane 0 is always a head
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const CellObs o = obs_shfl_up(v, d);
+    if (lane - d >= s) v = obs_combine(o, v);
+  }
+  const bool emit = tail && key != INV;
+  const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
+  if (emit) {
+    const uint32_t bucket = key >> kBucketBits;
+    // one cursor atomic per (warp, bucket); scratch, not map state
+    const uint32_t peers = __match_any_sync(emit_m, bucket);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&p.tb.bucket_cursor[bucket], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t slot = p.tb.bucket_offset[bucket] + base + __popc(peers & ((1u << lane) - 1u));
+    uint4* dst = reinterpret_cast<uint4*>(p.tb.records + slot);
+    dst[0] = make_uint4(key & (kBucketCells - 1u), __float_as_uint(v.mz), __float_as_uint(v.mv), v.mi);
+    dst[1] = make_uint4(__float_as_uint(v.xz), __float_as_uint(v.it), v.fi, v.li);
+  }
+}
+
+// ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
+struct TileSmem {
+  CellRecord stage[kChunk];          // TMA destination
+  uint32_t binoff[kBucketCells];     // counting-sort bins (count -> offset -> cursor)
+  float a_mz[kBucketCells];          // per-cell accumulators for the whole bucket
+  float a_mv[kBucketCells];
+  uint32_t a_mi[kBucketCells];
+  float a_xz[kBucketCells];
+  float a_it[kBucketCells];
+  uint32_t a_fi[kBucketCells];
+  uint32_t a_li[kBucketCells];
+  uint16_t perm[kChunk];             // sorted position -> index into stage
+  uint16_t tlist[kBucketCells];      // compacted list of the bucket's touched cells
+  uint64_t mbar;
+  uint32_t warp_sums[kWarps];
+  uint32_t n_touched;
+  uint32_t list_base;
+  uint32_t is_last;
+};
+
+__global__ void __launch_bounds__(kThreads, 3)
+tile_estimate_kernel(const __grid_constant__ EstimateParams p,
+                     const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters,
+                     DeviceState* __restrict__ st_out, const __grid_constant__ PublishArgs pub) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) mbar_init(&S.mbar, 1);
+  uint32_t phase = 0;
+  const uint32_t n_jobs = counters[CNT_BUCKETS];
+
+  // static round-robin over the non-empty buckets K2 listed: no work-fetch atomics
+  for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    __syncthreads();  // previous bucket completely done (also publishes the mbarrier init)
+    const uint4 entry = tb.bucket_list[job];  // {bucket, first record slot, points, -}
+    const uint32_t b = entry.x;
+    const uint32_t off = entry.y;
+    // Stage the first chunk right away.  The record count is not known yet (it is being
+    // loaded below); the bucket's POINT count bounds it and the segment has that many
+    // slots, so copying min(points, chunk) records is in bounds and always enough.
+    const uint32_t first_n = min(entry.z, static_cast<uint32_t>(kChunk));
+    if (tid == 0) {
+      fence_proxy_async();  // earlier generic-proxy reads of `stage` precede the async write
+      mbar_expect_tx(&S.mbar, first_n * static_cast<uint32_t>(sizeof(CellRecord)));
+      tma_load_1d(S.stage, tb.records + off, first_n * static_cast<uint32_t>(sizeof(CellRecord)),
+                  &S.mbar);
+    }
+    const uint32_t nrec = tb.bucket_cursor[b];  // in flight together with the bulk copy
+
+    for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
+      S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
+      S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
+      S.binoff[c] = 0;
+    }
+    if (tid == 0) S.n_touched = 0;
+
+    for (uint32_t cs = 0; cs < nrec; cs += kChunk) {
+      const uint32_t cn = min(static_cast<uint32_t>(kChunk), nrec - cs);
+      if (cs > 0) {
+        // overflow chunks of a crowded bucket: same staging buffer, exact byte count
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&S.mbar, cn * static_cast<uint32_t>(sizeof(CellRecord)));
+          tma_load_1d(S.stage, tb.records + off + cs,
+                      cn * static_cast<uint32_t>(sizeof(CellRecord)), &S.mbar);
+        }
+        for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) S.binoff[c] = 0;
+      }
+      __syncthreads();
+      mbar_wait(&S.mbar, phase);
+      phase ^= 1;
+
+      // ── counting sort by cell, in shared memory ──
+      for (uint32_t e = tid; e < cn; e += kThreads) atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
+      __syncthreads();
+      {
+        // exclusive scan of the 1024 bins: 4 consecutive bins per thread
+        const uint32_t v0 = S.binoff[tid * 4 + 0], v1 = S.binoff[tid * 4 + 1];
+        const uint32_t v2 = S.binoff[tid * 4 + 2], v3 = S.binoff[tid * 4 + 3];
+        const uint32_t t = v0 + v1 + v2 + v3;
+        uint32_t inc = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += o;
+        }
+        if (lane == 31) S.warp_sums[warp] = inc;
+        __syncthreads();
+        uint32_t wprefix = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+          if (w < warp) wprefix += S.warp_sums[w];
+        const uint32_t base = wprefix + inc - t;
+        S.binoff[tid * 4 + 0] = base;
+        S.binoff[tid * 4 + 1] = base + v0;
+        S.binoff[tid * 4 + 2] = base + v0 + v1;
+        S.binoff[tid * 4 + 3] = base + v0 + v1 + v2;
+      }
+      __syncthreads();
+      for (uint32_t e = tid; e < cn; e += kThreads) {
+        const uint32_t pos = atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
+        S.perm[pos] = static_cast<uint16_t>(e);
+      }
+      __syncthreads();
+
+      // ── warp-segmented reduce over the sorted order ──
+      // warp w owns the segments whose first sorted element lies in [wb, we) and follows
+      // them past `we` if needed, so each cell of the chunk is merged by exactly one lane
+      const uint32_t per = ((cn + kThreads - 1) / kThreads) * 32u;
+      const uint32_t wb = warp * per;
+      const uint32_t we = min(wb + per, cn);
+      if (wb < cn) {
+        bool open = false;
+        CellObs carry = obs_identity();
+        for (uint32_t base = wb;; base += 32) {
+          const uint32_t j = base + lane;
+          const bool valid = j < cn;
+          uint32_t k = kNone;
+          CellObs v = obs_identity();
+          if (valid) {
+            const CellRecord& r = S.stage[S.perm[j]];
+            k = r.lkey;
+            v = obs_of(r);
+          }
+          uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+          if (lane == 0) kprev = (j > 0 && valid) ? S.stage[S.perm[j - 1]].lkey : kNone;
+          uint32_t knext = __shfl_down_sync(0xffffffffu, k, 1);
+          if (lane == 31) knext = (j + 1 < cn) ? S.stage[S.perm[j + 1]].lkey : kNone;
+          const bool head = valid && (j == 0 || k != kprev);
+          const bool tail = valid && (j + 1 >= cn || k != knext);
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          const uint32_t m = heads & (0xffffffffu >> (31 - lane));
+          const bool head_in_win = m != 0;
+          const int s = head_in_win ? (31 - __clz(m)) : 0;
+          const bool owned = valid && (head_in_win ? (base + s < we) : open);
+          if (!owned) v = obs_identity();
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const CellObs o = obs_shfl_up(v, d);
+            if (lane - d >= s) v = obs_combine(o, v);
+          }
+          if (!head_in_win && open) v = obs_combine(carry, v);
+          if (owned && tail) {
+            // merge into the bucket's accumulator for this cell (sole writer in this chunk)
+            CellObs a;
+            a.mz = S.a_mz[k]; a.mv = S.a_mv[k]; a.mi = S.a_mi[k]; a.xz = S.a_xz[k];
+            a.it = S.a_it[k]; a.fi = S.a_fi[k]; a.li = S.a_li[k];
+            a = obs_combine(a, v);
+            S.a_mz[k] = a.mz; S.a_mv[k] = a.mv; S.a_mi[k] = a.mi; S.a_xz[k] = a.xz;
+            S.a_it[k] = a.it; S.a_fi[k] = a.fi; S.a_li[k] = a.li;
+          }
+          const uint32_t remaining = cn - base;
+          const int last_lane = remaining >= 32 ? 31 : static_cast<int>(remaining) - 1;
+          const bool last_tail = __shfl_sync(0xffffffffu, tail, last_lane);
+          const bool last_owned = __shfl_sync(0xffffffffu, owned, last_lane);
+          carry = obs_shfl(v, last_lane);
+          open = last_owned && !last_tail;
+          if (remaining <= 32) break;
+          if (base + 32 >= we && !open) break;
+        }
+      }
+      __syncthreads();  // accumulators + stage reads done before the next chunk / final pass
+    }
+
+    // ── compact the bucket's touched cells (ascending by construction of the ranks) ──
+#pragma unroll
+    for (int r = 0; r < static_cast<int>(kBucketCells) / kThreads; ++r) {
+      const int c = tid + r * kThreads;
+      const bool touched = S.a_fi[c] != kNone;
+      const uint32_t tm = __ballot_sync(0xffffffffu, touched);
+      uint32_t wbase = 0;
+      if (lane == 0 && tm) wbase = atomicAdd(&S.n_touched, __popc(tm));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (touched) S.tlist[wbase + __popc(tm & ((1u << lane) - 1u))] = static_cast<uint16_t>(c);
+    }
+    __syncthreads();
+    const uint32_t nt = S.n_touched;
+    if (tid == 0) {
+      // reserve this bucket's slice of the touched-cell list (next scan's obstacle reset)
+      // and count the cells; the round trip overlaps the estimator work below
+      S.list_base = nt ? atomicAdd(&st_out->touched_count, nt) : 0u;
+      if (nt) atomicAdd(&counters[CNT_CELLS], nt);
+      tb.bucket_count[b] = 0;   // re-arm the L1 scratch for the next scan
+      tb.bucket_cursor[b] = 0;
+    }
+
+    // ── estimator: one Kalman / P2 step per touched cell; each layer value is loaded once
+    //    (batched) and stored once; neighbouring threads handle neighbouring cells ──
+    const uint32_t key_base = b << kBucketBits;
+    for (uint32_t t = tid; t < nt; t += kThreads) {
+      const uint32_t c = S.tlist[t];
+      CellObs v;
+      v.mz = S.a_mz[c]; v.mv = S.a_mv[c]; v.mi = S.a_mi[c]; v.xz = S.a_xz[c];
+      v.it = S.a_it[c]; v.fi = S.a_fi[c]; v.li = S.a_li[c];
+      apply_observation(p, key_base + c, v);
+    }
+    __syncthreads();
+    const uint32_t lb = S.list_base;
+    for (uint32_t t = tid; t < nt; t += kThreads) {
+      const uint32_t c = S.tlist[t];
+      p.touched_keys[lb + t] = key_base + c;
+      if (p.touched_minz) p.touched_minz[lb + t] = S.a_mz[c];
+    }
+  }
+
+  // ── end of scan: the LAST CTA to finish publishes (no extra kernel / memset / memcpy):
+  // scan statistics + committed state go to the host through mapped pinned memory, the
+  // committed state becomes current, and the counters are re-armed for the next scan ──
+  if (pub.enabled) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      S.is_last = (atomicAdd(&counters[CNT_WORK], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (S.is_last && warp == 0) {
+      __threadfence();
+      constexpr int kStateWords = sizeof(DeviceState) / 4;
+      static_assert(kStateWords <= 32 && CNT_COUNT <= 32, "one warp publishes");
+      volatile uint32_t* vc = counters;
+      volatile const uint32_t* vs = reinterpret_cast<const uint32_t*>(st_out);
+      uint32_t c = 0, w = 0;
+      if (lane < CNT_COUNT) c = vc[lane];
+      if (lane < kStateWords) w = vs[lane];
+      if (lane < CNT_COUNT) {
+        pub.host_out[lane] = c;
+        counters[lane] = 0;
+      }
+      if (lane < kStateWords) {
+        pub.host_out[CNT_COUNT + lane] = w;
+        reinterpret_cast<uint32_t*>(pub.st_cur)[lane] = w;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int tile_estimate_configure() {
+  return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(sizeof(TileSmem))));
+}
+
+void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc) {
+  if (p.n == 0) return;
+  scatter_records_kernel<<<(p.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(p);
+  ++lc.mine;
+}
+
+void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
+                          DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
+                          LaunchCounter& lc) {
+  // CTAs stride over the non-empty-bucket list; 3 CTAs/SM fit in shared memory
+  const uint32_t grid = min(tb.n_buckets, 148u * 3u);
+  tile_estimate_kernel<<<grid, kThreads, sizeof(TileSmem), s>>>(p, tb, counters, st_out, pub);
+  ++lc.mine;
+}
+
+}  // namespace fdem
+
+namespace fdem {
+KernelDesc desc_scatter_records(uint32_t n) {
+  return KernelDesc{reinterpret_cast<const void*>(&scatter_records_kernel),
+                    dim3((n + kThreads - 1) / kThreads), dim3(kThreads), 0};
+}
+KernelDesc desc_tile_estimate(uint32_t n_buckets) {
+  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel),
+                    dim3(n_buckets < 148u * 3u ? n_buckets : 148u * 3u), dim3(kThreads),
+                    sizeof(TileSmem)};
+}
+}  // namespace fdem

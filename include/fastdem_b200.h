@@ -249,6 +249,29 @@ fdem_status fdem_inpaint(fdem_map* map, int32_t max_iterations, int32_t min_vali
                          int32_t inplace);
 
 /* ── instrumentation ──────────────────────────────────────────────────────── */
+/* pipeline stages of one scan, in stream order */
+enum {
+  FDEM_STAGE_H2D = 0,        /* host -> device staging of the cloud (0 when inputs are device) */
+  FDEM_STAGE_PREPROCESS = 1, /* K1 preprocess_bin_kernel                                       */
+  FDEM_STAGE_COMMIT = 2,     /* K2 commit_move_clear_kernel                                    */
+  FDEM_STAGE_SORT = 3,       /* sort by cell                                                   */
+  FDEM_STAGE_ESTIMATE = 4,   /* K3 segreduce_estimate_kernel                                   */
+  FDEM_STAGE_RAYCAST = 5,    /* voxelGrid(ANY) + raycasting (0 when disabled)                  */
+  FDEM_STAGE_COUNT = 6
+};
+/* When enabled, every scan brackets its stages with CUDA events on the map's stream;
+ * fdem_mapper_stage_times() returns the accumulated device milliseconds per stage and the
+ * number of scans accumulated, and resets the accumulators.  Implies a stream sync. */
+fdem_status fdem_mapper_set_stage_timing(fdem_mapper* m, int32_t enabled);
+fdem_status fdem_mapper_stage_times(fdem_mapper* m, double ms[FDEM_STAGE_COUNT], int64_t* scans);
+/* Which sort-by-cell implementation the mapper uses (results are identical):
+ *   TILE   (default) 2-level sort: bucket partition + per-bucket shared-memory sort and
+ *          warp-segmented reduce, TMA-staged (kernels_tile.cu)
+ *   GLOBAL one CUB radix sort of the whole scan + warp-segmented reduce (kernels.cu) */
+enum { FDEM_CELL_SORT_TILE = 0, FDEM_CELL_SORT_GLOBAL = 1 };
+fdem_status fdem_mapper_set_cell_sort(fdem_mapper* m, int32_t mode);
+/* kernels launched through CUB (radix-sort passes) since the map was created */
+fdem_status fdem_mapper_library_launch_count(fdem_mapper* m, int64_t* launches);
 /* number of kernels THIS library launched since the handle was created (bench.py's
  * gpu_launches) */
 fdem_status fdem_mapper_launch_count(fdem_mapper* m, int64_t* launches);

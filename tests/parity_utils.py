@@ -48,13 +48,15 @@ def compare_maps(gpu_map, omap, layers=None, rtol=RTOL, atol=ATOL):
     return report
 
 
-def run_pair(fdem, wl, n_scans, cfg=None, scan_fn=None):
+def run_pair(fdem, wl, n_scans, cfg=None, scan_fn=None, cell_sort=None):
     """Integrate n_scans synthetic scans of workload `wl` on both paths.  Returns
     (gpu_map, oracle_map, [gpu stats], [oracle stats])."""
     from fastdem_b200 import synthetic as syn
     cfg = cfg if cfg is not None else wl.config()
     gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
     gdem = fdem.FastDEM(gmap, cfg)
+    if cell_sort is not None:
+        gdem.set_cell_sort(cell_sort)
     omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
     odem = ob.OracleFastDEM(omap, cfg)
     gs, os_ = [], []

@@ -10,15 +10,16 @@ from parity_utils import compare_maps, run_pair
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("cell_sort", [0, 1], ids=["tile", "global"])
 @pytest.mark.parametrize("name,n_scans", [
     ("tiny", 12),
     ("c1_vlp16_local", 8),       # BASELINE configs[0]: the reference's CPU-runnable case
     ("c2_lidar64_local", 6),     # configs[1]: the bench workload
     ("c3_rgbd_p2", 7),           # configs[2]: RGBD model + P2 (needs > 5 scans to leave phase 1)
 ])
-def test_workload_parity(fdem, name, n_scans):
+def test_workload_parity(fdem, name, n_scans, cell_sort):
     wl = syn.WORKLOADS[name]
-    gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, n_scans)
+    gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, n_scans, cell_sort=cell_sort)
     report = compare_maps(gmap, omap)
     touched = int(np.isfinite(omap.get("elevation")).sum())
     assert touched > 0
