@@ -521,6 +521,26 @@ class FastDEM:
             Twb.ctypes.data_as(C.POINTER(C.c_double))))
         self._keep = keep
 
+    def submit(self, cloud: PointCloud, T_base_sensor, T_world_base) -> int:
+        """Queue one scan; returns its ticket.  `submit(k+1); collect(k)` overlaps the
+        host->device copy of scan k+1 with the kernels of scan k."""
+        n, pxyzw, pint, prgb, keep = self._channels(cloud)
+        Tbs, Twb = _iso(T_base_sensor), _iso(T_world_base)
+        t = C.c_uint64()
+        check(self._lib.fdem_mapper_submit(
+            self._h, pxyzw, pint, prgb, n, Tbs.ctypes.data_as(C.POINTER(C.c_double)),
+            Twb.ctypes.data_as(C.POINTER(C.c_double)), C.byref(t)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[t.value] = keep
+        return t.value
+
+    def collect(self, ticket: int) -> FdemScanStats:
+        stats = FdemScanStats()
+        check(self._lib.fdem_mapper_collect(self._h, ticket, C.byref(stats)))
+        getattr(self, "_inflight", {}).pop(ticket, None)
+        return stats
+
     def wait(self) -> FdemScanStats:
         stats = FdemScanStats()
         check(self._lib.fdem_mapper_wait(self._h, C.byref(stats)))
@@ -561,6 +581,11 @@ class FastDEM:
         xyz = np.empty((max(nc.value, 1), 3), np.float32)
         check(self._lib.fdem_mapper_last_rasterized(self._h, xyz.ctypes.data, C.byref(nc)))
         return PointCloud(xyz[:nc.value], frame_id=self._map.getFrameId())
+
+    def debug_phase_clocks(self):
+        out = (C.c_int64 * 16)()
+        check(self._lib.fdem_mapper_debug_phase_clocks(self._h, out))
+        return list(out)
 
     def set_cell_sort(self, mode: int) -> None:
         """capi.CELL_SORT_TILE (default) or capi.CELL_SORT_GLOBAL; results are identical."""

@@ -102,6 +102,8 @@ SIGNATURES = {
                                     C.POINTER(FdemScanStats)]),
     "fdem_mapper_integrate_async": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p]),
     "fdem_mapper_wait": (_ST, [_P, C.POINTER(FdemScanStats)]),
+    "fdem_mapper_submit": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p, C.POINTER(C.c_uint64)]),
+    "fdem_mapper_collect": (_ST, [_P, C.c_uint64, C.POINTER(FdemScanStats)]),
     "fdem_mapper_update": (_ST, [_P, _f32p, _f32p, _f32p, _u8p, C.c_size_t, C.c_double, C.c_double,
                                  C.POINTER(FdemScanStats)]),
     "fdem_mapper_integrate_with_cov": (_ST, [_P, _f32p, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p,
@@ -115,6 +117,7 @@ SIGNATURES = {
     "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),
     "fdem_mapper_set_cell_sort": (_ST, [_P, C.c_int32]),
+    "fdem_mapper_debug_phase_clocks": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_stage_times": (_ST, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

@@ -72,6 +72,9 @@ struct ScanResult {
 
 }  // namespace
 
+constexpr int kResultRing = 8;   // scans that may be in flight before a result slot is reused
+constexpr int kStageRing = 2;    // host-input staging buffers (copy of scan k+1 overlaps scan k)
+
 struct fdem_map {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -91,8 +94,12 @@ struct fdem_map {
   uint32_t* d_hits = nullptr;
   // small scratch
   uint32_t* d_flag = nullptr;
-  ScanResult* h_result = nullptr;  // pinned + mapped: the publish kernel writes it directly
-  uint32_t* d_result_host = nullptr;  // device-side alias of h_result
+  // ring of result slots in pinned + mapped host memory: the kernel that ends scan q writes
+  // slot q % kResultRing directly; ev_scan[q % kResultRing] marks that scan's completion
+  ScanResult* h_result = nullptr;
+  uint32_t* d_result_host = nullptr;  // device-side alias of h_result[0]
+  cudaEvent_t ev_scan[kResultRing] = {};
+  uint64_t seq = 0;                   // scans enqueued so far (ticket of the next scan)
   LaunchCounter lc;
 };
 
@@ -128,10 +135,14 @@ struct fdem_mapper {
   fdem_map* map = nullptr;
   fdem_config cfg{};
   size_t cap = 0;  // scratch capacity in points
-  float4* d_in_xyzw = nullptr;
-  float* d_in_intensity = nullptr;
-  uint8_t* d_in_rgb = nullptr;
-  float* d_in_aux = nullptr;  // cov9 (N x 9) or var_z (N)
+  // host-input staging, double buffered: slot q % kStageRing of scan q
+  float4* d_in_xyzw[kStageRing] = {};
+  float* d_in_intensity[kStageRing] = {};
+  uint8_t* d_in_rgb[kStageRing] = {};
+  float* d_in_aux[kStageRing] = {};  // cov9 (N x 9) or var_z (N)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[kStageRing] = {};
+  uint64_t last_ticket = 0;
   float4* d_pm = nullptr;
   uint32_t *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr, *d_svals = nullptr;
   uint64_t *d_vkeys = nullptr, *d_svkeys = nullptr;  // voxel keys (raycasting)
@@ -146,6 +157,7 @@ struct fdem_mapper {
   // tile path (2-level sort-by-cell); global CUB sort kept as the alternative path
   bool use_tile = true;
   bool use_graph = true;   // launch the tile pipeline as one CUDA graph (FDEM_GRAPH=0 disables)
+  bool use_pdl = false;    // programmatic edges between the graph's kernels (FDEM_PDL=1 enables)
   bool counters_dirty = true;
   ScanLaunch launch{};
   ScanGraph sg;
@@ -305,10 +317,14 @@ fdem_status validate_config(const fdem_config* c) {
 }
 
 void free_scratch(fdem_mapper* mp) {
-  cudaFree(mp->d_in_xyzw);
-  cudaFree(mp->d_in_intensity);
-  cudaFree(mp->d_in_rgb);
-  cudaFree(mp->d_in_aux);
+  for (int i = 0; i < kStageRing; ++i) {
+    cudaFree(mp->d_in_xyzw[i]);
+    cudaFree(mp->d_in_intensity[i]);
+    cudaFree(mp->d_in_rgb[i]);
+    cudaFree(mp->d_in_aux[i]);
+    mp->d_in_xyzw[i] = nullptr; mp->d_in_intensity[i] = nullptr;
+    mp->d_in_rgb[i] = nullptr; mp->d_in_aux[i] = nullptr;
+  }
   cudaFree(mp->d_pm);
   cudaFree(mp->d_keys);
   cudaFree(mp->d_vals);
@@ -320,8 +336,7 @@ void free_scratch(fdem_mapper* mp) {
   cudaFree(mp->d_sort_temp);
   cudaFree(mp->tb.records);
   mp->tb.records = nullptr;
-  mp->d_in_xyzw = nullptr; mp->d_in_intensity = nullptr; mp->d_in_rgb = nullptr;
-  mp->d_in_aux = nullptr; mp->d_pm = nullptr; mp->d_keys = mp->d_vals = nullptr;
+  mp->d_pm = nullptr; mp->d_keys = mp->d_vals = nullptr;
   mp->d_skeys = mp->d_svals = nullptr; mp->d_vkeys = mp->d_svkeys = nullptr;
   mp->d_sel = nullptr; mp->d_sort_temp = nullptr;
   mp->cap = 0;
@@ -335,12 +350,15 @@ fdem_status ensure_capacity(fdem_mapper* mp, size_t n) {
     return FDEM_OK;
   }
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));  // scratch may still be in use
+  if (mp->copy_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->copy_stream));
   const size_t cap = std::max<size_t>(std::max(n, mp->cap), 1024);
   free_scratch(mp);
-  FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_xyzw, cap * sizeof(float4)));
-  FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_intensity, cap * sizeof(float)));
-  FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_rgb, cap * 3 + 16));
-  FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_aux, cap * 9 * sizeof(float)));
+  for (int i = 0; i < kStageRing; ++i) {
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_xyzw[i], cap * sizeof(float4)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_intensity[i], cap * sizeof(float)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_rgb[i], cap * 3 + 16));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_aux[i], cap * 9 * sizeof(float)));
+  }
   FDEM_CUDA_TRY(cudaMalloc(&mp->d_pm, cap * sizeof(float4)));
   FDEM_CUDA_TRY(cudaMalloc(&mp->d_keys, cap * sizeof(uint32_t)));
   FDEM_CUDA_TRY(cudaMalloc(&mp->d_vals, cap * sizeof(uint32_t)));
@@ -490,19 +508,43 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   if (in.rgb) FDEM_TRY(ensure_layer(m, "color", kNaN));
 
   PreprocessParams pp{};
-  const float* xyzw_d = nullptr;
-  FDEM_TRY(stage(in.xyzw, reinterpret_cast<float*>(mp->d_in_xyzw), static_cast<size_t>(n) * 4, s,
-                 &xyzw_d));
+  // Inputs already on the device are used in place.  Host inputs are copied into staging
+  // slot (ticket % kStageRing) on a separate copy stream, so the copy of scan k+1 overlaps
+  // the kernels of scan k; the compute stream waits for the copy through an event.
+  FDEM_REQUIRE(!(in.cov9 && in.var_z), "cov9 and var_z are exclusive");
+  const uint64_t ticket = m->seq;
+  const int slot = static_cast<int>(ticket % kStageRing);
+  const bool overlap = !mp->stage_timing;  // stage timing wants the copy on the timed stream
+  cudaStream_t cs = overlap ? mp->copy_stream : s;
+  bool staged = false;
+  auto stage_in = [&](const void* src, void* scratch, size_t bytes, const void** out) -> fdem_status {
+    if (!src) { *out = nullptr; return FDEM_OK; }
+    if (is_device_pointer(src)) { *out = src; return FDEM_OK; }
+    if (!staged && overlap && ticket >= kStageRing) {
+      // the slot's previous user (scan ticket - kStageRing) must be done with the buffers
+      FDEM_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_scan[(ticket - kStageRing) % kResultRing], 0));
+    }
+    staged = true;
+    FDEM_CUDA_TRY(cudaMemcpyAsync(scratch, src, bytes, cudaMemcpyHostToDevice, cs));
+    *out = scratch;
+    return FDEM_OK;
+  };
+  const void *xyzw_v = nullptr, *inten_v = nullptr, *rgb_v = nullptr, *aux_v = nullptr;
+  FDEM_TRY(stage_in(in.xyzw, mp->d_in_xyzw[slot], static_cast<size_t>(n) * 16, &xyzw_v));
+  FDEM_TRY(stage_in(in.intensity, mp->d_in_intensity[slot], static_cast<size_t>(n) * 4, &inten_v));
+  FDEM_TRY(stage_in(in.rgb, mp->d_in_rgb[slot], static_cast<size_t>(n) * 3, &rgb_v));
+  if (in.cov9) FDEM_TRY(stage_in(in.cov9, mp->d_in_aux[slot], static_cast<size_t>(n) * 36, &aux_v));
+  if (in.var_z) FDEM_TRY(stage_in(in.var_z, mp->d_in_aux[slot], static_cast<size_t>(n) * 4, &aux_v));
+  if (staged && overlap) {
+    FDEM_CUDA_TRY(cudaEventRecord(mp->ev_copied[slot], cs));
+    FDEM_CUDA_TRY(cudaStreamWaitEvent(s, mp->ev_copied[slot], 0));
+  }
+  const float* xyzw_d = static_cast<const float*>(xyzw_v);
+  const float* inten_d = static_cast<const float*>(inten_v);
+  const uint8_t* rgb_d = static_cast<const uint8_t*>(rgb_v);
+  const float* aux_d = static_cast<const float*>(aux_v);
   FDEM_REQUIRE((reinterpret_cast<uintptr_t>(xyzw_d) & 15) == 0, "xyzw must be 16-byte aligned");
   pp.xyzw = reinterpret_cast<const float4*>(xyzw_d);
-  const float* inten_d = nullptr;
-  FDEM_TRY(stage(in.intensity, mp->d_in_intensity, n, s, &inten_d));
-  const uint8_t* rgb_d = nullptr;
-  FDEM_TRY(stage(in.rgb, mp->d_in_rgb, static_cast<size_t>(n) * 3, s, &rgb_d));
-  FDEM_REQUIRE(!(in.cov9 && in.var_z), "cov9 and var_z are exclusive");
-  const float* aux_d = nullptr;
-  if (in.cov9) FDEM_TRY(stage(in.cov9, mp->d_in_aux, static_cast<size_t>(n) * 9, s, &aux_d));
-  if (in.var_z) FDEM_TRY(stage(in.var_z, mp->d_in_aux, n, s, &aux_d));
   pp.intensity = inten_d;
   pp.cov9 = in.cov9 ? aux_d : nullptr;
   pp.var_z = in.var_z ? aux_d : nullptr;
@@ -615,14 +657,15 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   L.pm = mp->d_pm;
   L.keys = mp->d_keys;
   L.vals = mp->d_vals;
-  L.host_out = m->d_result_host;
+  uint32_t* host_slot = m->d_result_host + (ticket % kResultRing) * (sizeof(ScanResult) / 4);
+  L.host_out = host_slot;
 
   const bool raycast = cfg.raycasting_enabled && in.input_frame == INPUT_SENSOR_FRAME;
   // K3t's last CTA ends the scan itself unless more kernels follow (raycasting)
   L.pub = PublishArgs{};
   L.pub.enabled = (tile && !raycast) ? 1 : 0;
   L.pub.st_cur = m->d_state;
-  L.pub.host_out = m->d_result_host;
+  L.pub.host_out = host_slot;
   const bool graph = tile && mp->use_graph && !mp->stage_timing && !raycast;
   fdem_status launch_status = FDEM_OK;
   if (graph) {
@@ -669,7 +712,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
     mark(FDEM_STAGE_COUNT);
     // counters + committed state -> host (mapped pinned memory), state made current, counters re-armed
     if (!L.pub.enabled)
-      launch_publish(mp->d_counters, m->d_state, m->d_state + 1, m->d_result_host, s, m->lc);
+      launch_publish(mp->d_counters, m->d_state, m->d_state + 1, host_slot, s, m->lc);
   }
   {
     cudaError_t le = cudaGetLastError();
@@ -681,6 +724,9 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
       return launch_status;
     }
   }
+  FDEM_CUDA_TRY(cudaEventRecord(m->ev_scan[ticket % kResultRing], s));
+  m->seq = ticket + 1;
+  mp->last_ticket = ticket;
   m->geom_stale = true;
   mp->last_n = n;
   mp->last_had_work = true;
@@ -735,8 +781,17 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
     FDEM_CUDA_TRY(cudaGraphCreate(&G.graph, 0));
     for (int i = 0; i < GN_COUNT; ++i) {
       cudaKernelNodeParams kp = node_params(na[i]);
-      FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i], G.graph, i ? &G.node[i - 1] : nullptr,
-                                           i ? 1 : 0, &kp));
+      FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i], G.graph, nullptr, 0, &kp));
+    }
+    for (int i = 1; i < GN_COUNT; ++i) {
+      // programmatic edges: node i may launch as soon as node i-1 has called
+      // griddepcontrol.launch_dependents; it blocks at griddepcontrol.wait until i-1 is done
+      cudaGraphEdgeData ed{};
+      if (mp->use_pdl) {
+        ed.from_port = cudaGraphKernelNodePortProgrammatic;
+        ed.type = cudaGraphDependencyTypeProgrammatic;
+      }
+      FDEM_CUDA_TRY(cudaGraphAddDependencies_v2(G.graph, &G.node[i - 1], &G.node[i], &ed, 1));
     }
     FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
     G.cached = L;
@@ -770,7 +825,7 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
   if (!mp->ev_scans.empty()) drain_stage_events(mp);
   if (mp->last_had_work) {
-    const ScanResult& r = *m->h_result;
+    const ScanResult& r = m->h_result[mp->last_ticket % kResultRing];
     m->geom = r.state.geom;
     m->geom_stale = false;
     mp->last.n_input = mp->last_n;
@@ -890,9 +945,11 @@ fdem_status fdem_map_create_stripe(float width, float height, float resolution, 
   FDEM_CUDA_TRY(cudaMalloc(&m->d_state, 2 * sizeof(DeviceState)));
   FDEM_CUDA_TRY(cudaMemset(m->d_state, 0, 2 * sizeof(DeviceState)));
   FDEM_CUDA_TRY(cudaMalloc(&m->d_flag, 4 * sizeof(uint32_t)));
-  FDEM_CUDA_TRY(cudaHostAlloc(&m->h_result, sizeof(ScanResult), cudaHostAllocMapped));
-  std::memset(m->h_result, 0, sizeof(ScanResult));
+  FDEM_CUDA_TRY(cudaHostAlloc(&m->h_result, kResultRing * sizeof(ScanResult), cudaHostAllocMapped));
+  std::memset(m->h_result, 0, kResultRing * sizeof(ScanResult));
   FDEM_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->d_result_host), m->h_result, 0));
+  for (int i = 0; i < kResultRing; ++i)
+    FDEM_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_scan[i], cudaEventDisableTiming));
   fdem_status st = push_state(m, 0);
   if (st != FDEM_OK) return st;
   // ElevationMap() basic layers (elevation_map.hpp:99-103), then clearAll()
@@ -922,6 +979,8 @@ fdem_status fdem_map_destroy(fdem_map* m) {
   cudaFree(m->d_ray_min_enc);
   cudaFree(m->d_hits);
   cudaFreeHost(m->h_result);
+  for (cudaEvent_t e : m->ev_scan)
+    if (e) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->stream);
   delete m;
   return FDEM_OK;
@@ -1186,11 +1245,22 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
   cudaError_t e = cudaMalloc(&mp->d_counters, CNT_COUNT * sizeof(uint32_t));
   if (e != cudaSuccess) { delete mp; return set_error(FDEM_ERR_CUDA, cudaGetErrorString(e)); }
   {
+    cudaError_t e3 = cudaStreamCreateWithFlags(&mp->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < kStageRing && e3 == cudaSuccess; ++i)
+      e3 = cudaEventCreateWithFlags(&mp->ev_copied[i], cudaEventDisableTiming);
+    if (e3 != cudaSuccess) {
+      fdem_mapper_destroy(mp);
+      return set_error(FDEM_ERR_CUDA, std::string("copy stream setup failed: ") + cudaGetErrorString(e3));
+    }
+  }
+  {
     // tile path scratch: one counter / offset / cursor / list slot per 1024-cell bucket
     const char* env = std::getenv("FDEM_CELL_SORT");
     mp->use_tile = !(env && std::string(env) == "cub");
     const char* genv = std::getenv("FDEM_GRAPH");
     mp->use_graph = !(genv && std::string(genv) == "0");
+    const char* penv = std::getenv("FDEM_PDL");
+    mp->use_pdl = penv && std::string(penv) == "1";  // measured: no gain inside a graph; opt-in
     mp->tb.n_buckets = static_cast<uint32_t>((map->cells + kBucketCells - 1) >> kBucketBits);
     const size_t nb = std::max<size_t>(mp->tb.n_buckets, 1) * sizeof(uint32_t);
     cudaError_t e2 = cudaMalloc(&mp->tb.bucket_count, nb);
@@ -1211,8 +1281,12 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   if (!mp) return FDEM_OK;
   DeviceGuard dg(mp->map->device);
   cudaStreamSynchronize(mp->map->stream);
+  if (mp->copy_stream) cudaStreamSynchronize(mp->copy_stream);
   free_scratch(mp);
   destroy_scan_graph(mp);
+  for (cudaEvent_t e : mp->ev_copied)
+    if (e) cudaEventDestroy(e);
+  if (mp->copy_stream) cudaStreamDestroy(mp->copy_stream);
   cudaFree(mp->d_counters);
   cudaFree(mp->tb.bucket_count);
   cudaFree(mp->tb.bucket_offset);
@@ -1289,6 +1363,44 @@ fdem_status fdem_mapper_integrate_async(fdem_mapper* mp, const float* xyzw,
                                         const float* intensity, const uint8_t* rgb, size_t n,
                                         const double* Tbs, const double* Twb) {
   return integrate_common(mp, xyzw, nullptr, intensity, rgb, n, Tbs, Twb);
+}
+
+fdem_status fdem_mapper_submit(fdem_mapper* mp, const float* xyzw, const float* intensity,
+                               const uint8_t* rgb, size_t n, const double* Tbs, const double* Twb,
+                               uint64_t* ticket) {
+  FDEM_REQUIRE(mp && ticket, "null argument");
+  FDEM_REQUIRE(n > 0, "submit needs a non-empty cloud (integrate() returns false on empty input)");
+  const uint64_t before = mp->map->seq;
+  // never let the ring wrap over a result nobody has been able to collect yet
+  if (before >= kResultRing) {
+    DeviceGuard dg(mp->map->device);
+    FDEM_CUDA_TRY(cudaEventSynchronize(mp->map->ev_scan[(before - kResultRing + 1) % kResultRing]));
+  }
+  FDEM_TRY(integrate_common(mp, xyzw, nullptr, intensity, rgb, n, Tbs, Twb));
+  *ticket = before;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stats* stats) {
+  FDEM_REQUIRE(mp && stats, "null argument");
+  fdem_map* m = mp->map;
+  FDEM_REQUIRE(ticket < m->seq, "unknown ticket");
+  FDEM_REQUIRE(ticket + kResultRing > m->seq, "ticket expired: its result slot has been reused");
+  DeviceGuard dg(m->device);
+  FDEM_CUDA_TRY(cudaEventSynchronize(m->ev_scan[ticket % kResultRing]));
+  const ScanResult& r = m->h_result[ticket % kResultRing];
+  stats->n_input = 0;  // not retained per ticket
+  stats->n_kept = r.counters[CNT_KEPT];
+  stats->n_cells = r.counters[CNT_CELLS];
+  stats->n_voxels = r.counters[CNT_VOXELS];
+  stats->integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
+  stats->_pad = 0;
+  if (ticket + 1 == m->seq) {  // newest scan: its committed geometry is the map's geometry
+    m->geom = r.state.geom;
+    m->geom_stale = false;
+  }
+  if (stats->n_cells > 0) m->obstacle_full_clear = false;
+  return FDEM_OK;
 }
 
 fdem_status fdem_mapper_wait(fdem_mapper* mp, fdem_scan_stats* stats) {
@@ -1384,6 +1496,16 @@ fdem_status fdem_mapper_last_rasterized(fdem_mapper* mp, float* xyz, int64_t* n_
     ++k;
   }
   *n_cells = k;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* mp, int64_t* out16) {
+  FDEM_REQUIRE(mp && out16, "null argument");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  long long tmp[16];
+  FDEM_CUDA_TRY(static_cast<cudaError_t>(tile_estimate_debug_clocks(tmp)));
+  for (int i = 0; i < 16; ++i) out16[i] = tmp[i];
   return FDEM_OK;
 }
 

@@ -20,6 +20,16 @@ namespace fdem {
 
 __device__ __forceinline__ float nan_f32() { return __int_as_float(0x7fc00000); }
 
+// Programmatic dependent launch (PDL).  The scan's kernels form a chain in one CUDA graph
+// with programmatic edges: each kernel lets its successor start launching right away
+// (pdl_launch_dependents) and blocks at pdl_wait() until its predecessor has completed and
+// flushed — so launch latency and prologues overlap the predecessor instead of adding up.
+// Both are no-ops for a kernel launched without a programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ElevationMapping::CellObservation (mapping/elevation_mapping.hpp:26-34) plus the point
 // indices that decide rasterize()'s order-dependent choices:
 //   min_z_var  = variance of the LOWEST-index point attaining min_z  (strict `z < min_z`, :65-68)

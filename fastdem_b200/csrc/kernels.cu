@@ -137,6 +137,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   // so binning against the prospective geometry is always right.
   __shared__ GridGeom sg;
   __shared__ uint32_t s_kept, s_inside;
+  pdl_launch_dependents();  // K2 may start launching; it waits for this grid at its pdl_wait()
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   // the point load does not depend on the geometry: put it in flight first
@@ -223,32 +224,46 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
 
 // ───────────────────────────── K2: commit / move / clear ─────────────────────
 
+// vacated rows / columns (or the whole map) -> NaN on the selected layers.  The
+// (layer, cell) space is flattened so the stores spread evenly over the threads.
 __device__ __forceinline__ void clear_spans(const GridGeom& g, const MoveResult& mr,
                                             const LayerTable& lt, int policy, size_t tid,
                                             size_t nthreads) {
-  const int rows_local = g.row_end - g.row_begin;
+  const uint32_t rows_local = static_cast<uint32_t>(g.row_end - g.row_begin);
   const size_t cells = static_cast<size_t>(rows_local) * g.cols;
   const int n_layers = (policy == 1) ? 3 : lt.count;
-  for (int li = 0; li < n_layers; ++li) {
-    float* __restrict__ d = lt.ptr[(policy == 1) ? lt.basic[li] : li];
-    if (mr.clear_all) {
+  if (mr.clear_all) {
+    for (int li = 0; li < n_layers; ++li) {
+      float* __restrict__ d = lt.ptr[(policy == 1) ? lt.basic[li] : li];
       for (size_t c = tid; c < cells; c += nthreads) d[c] = nan_f32();
-      continue;
     }
-    for (int sidx = 0; sidx < mr.n_spans; ++sidx) {
-      const ClearSpan sp = mr.spans[sidx];
-      if (sp.axis == 0) {  // buffer rows [k, k+n) of every column (LOCAL maps are unsharded)
-        const size_t total = static_cast<size_t>(sp.n) * g.cols;
-        for (size_t t = tid; t < total; t += nthreads) {
-          const size_t c = t / sp.n;
-          const size_t r = sp.k + (t - c * sp.n);
-          d[c * rows_local + r] = nan_f32();
-        }
-      } else {  // buffer columns [k, k+n): contiguous in column-major storage
-        const size_t total = static_cast<size_t>(sp.n) * rows_local;
-        float* __restrict__ base = d + static_cast<size_t>(sp.k) * rows_local;
-        for (size_t t = tid; t < total; t += nthreads) base[t] = nan_f32();
-      }
+    return;
+  }
+  uint32_t span_size[4] = {0, 0, 0, 0};
+  uint32_t per_layer = 0;
+  for (int sidx = 0; sidx < mr.n_spans; ++sidx) {
+    const ClearSpan sp = mr.spans[sidx];
+    span_size[sidx] = static_cast<uint32_t>(sp.n) * (sp.axis == 0 ? static_cast<uint32_t>(g.cols) : rows_local);
+    per_layer += span_size[sidx];
+  }
+  if (per_layer == 0) return;
+  const size_t total = static_cast<size_t>(per_layer) * n_layers;
+  for (size_t w = tid; w < total; w += nthreads) {
+    const uint32_t li = static_cast<uint32_t>(w / per_layer);
+    uint32_t t = static_cast<uint32_t>(w - static_cast<size_t>(li) * per_layer);
+    int sidx = 0;
+    while (t >= span_size[sidx]) {
+      t -= span_size[sidx];
+      ++sidx;
+    }
+    const ClearSpan sp = mr.spans[sidx];
+    float* __restrict__ d = lt.ptr[(policy == 1) ? lt.basic[li] : li];
+    if (sp.axis == 0) {  // buffer rows [k, k+n) of every column (LOCAL maps are unsharded)
+      const uint32_t c = t / static_cast<uint32_t>(sp.n);
+      const uint32_t r = static_cast<uint32_t>(sp.k) + (t - c * static_cast<uint32_t>(sp.n));
+      d[static_cast<size_t>(c) * rows_local + r] = nan_f32();
+    } else {             // buffer columns [k, k+n): contiguous in column-major storage
+      d[static_cast<size_t>(sp.k) * rows_local + t] = nan_f32();
     }
   }
 }
@@ -265,6 +280,8 @@ commit_move_clear_kernel(const __grid_constant__ CommitParams p,
   //   group B  reset of the last observing scan's obstacle cells
   //   group C  state commit + circular-buffer move (vacated rows / columns -> NaN)
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();  // K1's counters / bucket histogram are complete and visible from here on
   const uint32_t nA = p.tile_path ? gridDim.x / 2 : 0;
   const uint32_t nB = p.tile_path ? 0 : gridDim.x / 2;  // tile path: the scatter grid does job B
   const uint32_t s_inside = counters[CNT_INSIDE];

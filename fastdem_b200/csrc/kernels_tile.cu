@@ -12,11 +12,12 @@
 //              one 32-byte CellRecord per run is written into its bucket's segment
 //   L2  tile_estimate_kernel, one CTA per non-empty bucket (dynamic work list):
 //         the bucket's records are staged into shared memory with TMA bulk copies
-//         (cp.async.bulk + mbarrier), counting-sorted by cell inside shared memory,
-//         reduced per cell with a warp-segmented shuffle scan, merged into per-cell
-//         accumulators, and finally thread t applies the Kalman / P2 step to cell
-//         (bucket base + t): layer loads and stores are fully coalesced and each touched
-//         cell of each layer is written exactly once, with plain stores.
+//         (cp.async.bulk + mbarrier), counting-sorted by cell inside shared memory, and
+//         folded per cell into shared-memory accumulators — the owner thread walks a
+//         cell's (few) sorted records; crowded cells get a warp and a shuffle butterfly.
+//         Then the bucket's touched cells are compacted and each gets ONE Kalman / P2
+//         step: every layer value is loaded once (batched) and stored once with a plain
+//         store, neighbouring threads on neighbouring cells.
 //
 // Atomics appear only on scan-sized scratch (bucket cursors, shared-memory bins, scan
 // statistics) — never on estimator state.  Results are independent of every ordering the
@@ -35,6 +36,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 1024;  // records staged per bulk copy (32 KiB)
 constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint32_t kHotCell = 48;  // records of one cell in one chunk above which a warp takes over
 
 // ── shared-memory / TMA plumbing (inline PTX; SASS: UBLKCP + SYNCS) ──────────────
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -82,6 +84,8 @@ __device__ __forceinline__ CellObs obs_of(const CellRecord& r) {
 // ───────────────────────────── L1: scatter into bucket segments ──────────────
 __global__ void __launch_bounds__(kThreads)
 scatter_records_kernel(const __grid_constant__ ScatterParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // K1 (keys, pm) and K2 (bucket segments) are complete from here on
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint32_t INV = p.invalid_key;
@@ -136,6 +140,11 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   }
 }
 
+// phase timeline of CTA 0's first bucket (SM clock ticks since kernel entry), for tuning:
+// read back through fdem_mapper_debug_phase_clocks().  One thread, a dozen clock reads.
+__device__ long long g_k3t_clocks[16];
+#define K3T_MARK(i) do { if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[i] = clock64() - t_entry; } while (0)
+
 // ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
 struct TileSmem {
   CellRecord stage[kChunk];          // TMA destination
@@ -154,6 +163,8 @@ struct TileSmem {
   uint32_t n_touched;
   uint32_t list_base;
   uint32_t is_last;
+  uint32_t n_hot;
+  uint16_t hot_cell[kChunk / kHotCell + 1];  // cells deferred to the warp-cooperative path
 };
 
 __global__ void __launch_bounds__(kThreads, 3)
@@ -165,9 +176,20 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const long long t_entry = clock64();
+  bool first_job = true;
 
+  // prologue that needs nothing from the scatter kernel: overlaps its tail under PDL
   if (tid == 0) mbar_init(&S.mbar, 1);
   uint32_t phase = 0;
+  for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
+    S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
+    S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
+    S.binoff[c] = 0;
+  }
+  if (tid == 0) { S.n_touched = 0; S.n_hot = 0; }
+  pdl_wait();  // the bucket segments are complete and visible from here on
+  K3T_MARK(0);   // prologue done
   const uint32_t n_jobs = counters[CNT_BUCKETS];
 
   // static round-robin over the non-empty buckets K2 listed: no work-fetch atomics
@@ -187,13 +209,8 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
                   &S.mbar);
     }
     const uint32_t nrec = tb.bucket_cursor[b];  // in flight together with the bulk copy
-
-    for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
-      S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
-      S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
-      S.binoff[c] = 0;
-    }
-    if (tid == 0) S.n_touched = 0;
+    K3T_MARK(1);  // job entry + record count loaded
+    if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[15] = nrec;
 
     for (uint32_t cs = 0; cs < nrec; cs += kChunk) {
       const uint32_t cn = min(static_cast<uint32_t>(kChunk), nrec - cs);
@@ -210,6 +227,7 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       __syncthreads();
       mbar_wait(&S.mbar, phase);
       phase ^= 1;
+      if (cs == 0) K3T_MARK(2);  // first chunk staged
 
       // ── counting sort by cell, in shared memory ──
       for (uint32_t e = tid; e < cn; e += kThreads) atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
@@ -243,65 +261,75 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
         S.perm[pos] = static_cast<uint16_t>(e);
       }
       __syncthreads();
+      if (cs == 0) K3T_MARK(3);  // first chunk counting-sorted
 
-      // ── warp-segmented reduce over the sorted order ──
-      // warp w owns the segments whose first sorted element lies in [wb, we) and follows
-      // them past `we` if needed, so each cell of the chunk is merged by exactly one lane
-      const uint32_t per = ((cn + kThreads - 1) / kThreads) * 32u;
-      const uint32_t wb = warp * per;
-      const uint32_t we = min(wb + per, cn);
-      if (wb < cn) {
-        bool open = false;
-        CellObs carry = obs_identity();
-        for (uint32_t base = wb;; base += 32) {
-          const uint32_t j = base + lane;
-          const bool valid = j < cn;
-          uint32_t k = kNone;
-          CellObs v = obs_identity();
-          if (valid) {
-            const CellRecord& r = S.stage[S.perm[j]];
-            k = r.lkey;
-            v = obs_of(r);
-          }
-          uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
-          if (lane == 0) kprev = (j > 0 && valid) ? S.stage[S.perm[j - 1]].lkey : kNone;
-          uint32_t knext = __shfl_down_sync(0xffffffffu, k, 1);
-          if (lane == 31) knext = (j + 1 < cn) ? S.stage[S.perm[j + 1]].lkey : kNone;
-          const bool head = valid && (j == 0 || k != kprev);
-          const bool tail = valid && (j + 1 >= cn || k != knext);
-          const uint32_t heads = __ballot_sync(0xffffffffu, head);
-          const uint32_t m = heads & (0xffffffffu >> (31 - lane));
-          const bool head_in_win = m != 0;
-          const int s = head_in_win ? (31 - __clz(m)) : 0;
-          const bool owned = valid && (head_in_win ? (base + s < we) : open);
-          if (!owned) v = obs_identity();
+      // ── per-cell reduction of the sorted chunk ──
+      // After the counting sort the records of cell c occupy sorted positions
+      // [binoff[c-1], binoff[c]).  Thread t owns cells t, t+256, t+512, t+768 of the
+      // bucket: it folds each cell's few records (pre-reduced runs, typically 0-3) into
+      // that cell's accumulator, which nobody else touches.  Cells with many records in
+      // this chunk are deferred to the warp-cooperative path below.
+      uint32_t my_hot = 0;  // bit r set: my r-th cell was deferred
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const CellObs o = obs_shfl_up(v, d);
-            if (lane - d >= s) v = obs_combine(o, v);
-          }
-          if (!head_in_win && open) v = obs_combine(carry, v);
-          if (owned && tail) {
-            // merge into the bucket's accumulator for this cell (sole writer in this chunk)
-            CellObs a;
-            a.mz = S.a_mz[k]; a.mv = S.a_mv[k]; a.mi = S.a_mi[k]; a.xz = S.a_xz[k];
-            a.it = S.a_it[k]; a.fi = S.a_fi[k]; a.li = S.a_li[k];
-            a = obs_combine(a, v);
-            S.a_mz[k] = a.mz; S.a_mv[k] = a.mv; S.a_mi[k] = a.mi; S.a_xz[k] = a.xz;
-            S.a_it[k] = a.it; S.a_fi[k] = a.fi; S.a_li[k] = a.li;
-          }
-          const uint32_t remaining = cn - base;
-          const int last_lane = remaining >= 32 ? 31 : static_cast<int>(remaining) - 1;
-          const bool last_tail = __shfl_sync(0xffffffffu, tail, last_lane);
-          const bool last_owned = __shfl_sync(0xffffffffu, owned, last_lane);
-          carry = obs_shfl(v, last_lane);
-          open = last_owned && !last_tail;
-          if (remaining <= 32) break;
-          if (base + 32 >= we && !open) break;
+      for (int r = 0; r < static_cast<int>(kBucketCells) / kThreads; ++r) {
+        const int c = tid + r * kThreads;
+        const uint32_t s0 = c ? S.binoff[c - 1] : 0u;
+        const uint32_t e0 = S.binoff[c];
+        const uint32_t cnt = e0 - s0;
+        if (cnt == 0) continue;
+        if (cnt > kHotCell) {
+          const uint32_t h = atomicAdd(&S.n_hot, 1u);
+          S.hot_cell[h] = static_cast<uint16_t>(c);
+          my_hot |= 1u << r;
+          continue;
         }
+        CellObs a;
+        a.mz = S.a_mz[c]; a.mv = S.a_mv[c]; a.mi = S.a_mi[c]; a.xz = S.a_xz[c];
+        a.it = S.a_it[c]; a.fi = S.a_fi[c]; a.li = S.a_li[c];
+        for (uint32_t j = s0; j < e0; ++j) a = obs_combine(a, obs_of(S.stage[S.perm[j]]));
+        S.a_mz[c] = a.mz; S.a_mv[c] = a.mv; S.a_mi[c] = a.mi; S.a_xz[c] = a.xz;
+        S.a_it[c] = a.it; S.a_fi[c] = a.fi; S.a_li[c] = a.li;
       }
+      __syncthreads();
+      const uint32_t n_hot = S.n_hot;
+      if (n_hot) {
+        // crowded cells: one warp per cell, lanes stride over its records, butterfly
+        // reduction over warp shuffles, lane 0 merges into the accumulator
+        for (uint32_t h = warp; h < n_hot; h += kWarps) {
+          const int c = S.hot_cell[h];
+          const uint32_t s0 = c ? S.binoff[c - 1] : 0u;
+          const uint32_t e0 = S.binoff[c];
+          CellObs a = obs_identity();
+          for (uint32_t j = s0 + lane; j < e0; j += 32) a = obs_combine(a, obs_of(S.stage[S.perm[j]]));
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            CellObs o;
+            o.mz = __shfl_xor_sync(0xffffffffu, a.mz, d);
+            o.mv = __shfl_xor_sync(0xffffffffu, a.mv, d);
+            o.mi = __shfl_xor_sync(0xffffffffu, a.mi, d);
+            o.xz = __shfl_xor_sync(0xffffffffu, a.xz, d);
+            o.it = __shfl_xor_sync(0xffffffffu, a.it, d);
+            o.fi = __shfl_xor_sync(0xffffffffu, a.fi, d);
+            o.li = __shfl_xor_sync(0xffffffffu, a.li, d);
+            a = obs_combine(a, o);
+          }
+          if (lane == 0) {
+            CellObs t;
+            t.mz = S.a_mz[c]; t.mv = S.a_mv[c]; t.mi = S.a_mi[c]; t.xz = S.a_xz[c];
+            t.it = S.a_it[c]; t.fi = S.a_fi[c]; t.li = S.a_li[c];
+            t = obs_combine(t, a);
+            S.a_mz[c] = t.mz; S.a_mv[c] = t.mv; S.a_mi[c] = t.mi; S.a_xz[c] = t.xz;
+            S.a_it[c] = t.it; S.a_fi[c] = t.fi; S.a_li[c] = t.li;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) S.n_hot = 0;
+      }
+      (void)my_hot;
       __syncthreads();  // accumulators + stage reads done before the next chunk / final pass
+      if (cs == 0) K3T_MARK(4);  // first chunk reduced
     }
+    K3T_MARK(5);  // all chunks done
 
     // ── compact the bucket's touched cells (ascending by construction of the ranks) ──
 #pragma unroll
@@ -316,6 +344,7 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
     }
     __syncthreads();
     const uint32_t nt = S.n_touched;
+    K3T_MARK(6);  // touched cells compacted
     if (tid == 0) {
       // reserve this bucket's slice of the touched-cell list (next scan's obstacle reset)
       // and count the cells; the round trip overlaps the estimator work below
@@ -336,17 +365,32 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       apply_observation(p, key_base + c, v);
     }
     __syncthreads();
+    K3T_MARK(7);  // estimator done
     const uint32_t lb = S.list_base;
     for (uint32_t t = tid; t < nt; t += kThreads) {
       const uint32_t c = S.tlist[t];
       p.touched_keys[lb + t] = key_base + c;
       if (p.touched_minz) p.touched_minz[lb + t] = S.a_mz[c];
     }
+    K3T_MARK(8);  // touched list written
+    first_job = false;
+    if (job + gridDim.x < n_jobs) {
+      // another bucket follows on this CTA: re-arm the accumulators and bins
+      __syncthreads();
+      for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
+        S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
+        S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
+        S.binoff[c] = 0;
+      }
+      if (tid == 0) S.n_touched = 0;
+    }
   }
 
   // ── end of scan: the LAST CTA to finish publishes (no extra kernel / memset / memcpy):
   // scan statistics + committed state go to the host through mapped pinned memory, the
   // committed state becomes current, and the counters are re-armed for the next scan ──
+  first_job = true;
+  K3T_MARK(9);  // all jobs of CTA 0 done
   if (pub.enabled) {
     __syncthreads();
     if (tid == 0) {
@@ -373,9 +417,14 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       }
     }
   }
+  K3T_MARK(10);  // kernel exit of CTA 0
 }
 
 }  // namespace
+
+int tile_estimate_debug_clocks(long long* out16) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out16, g_k3t_clocks, sizeof(long long) * 16));
+}
 
 int tile_estimate_configure() {
   return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel,

@@ -206,6 +206,15 @@ fdem_status fdem_mapper_integrate_async(fdem_mapper* m, const float* xyzw, const
                                         const double T_world_base[16]);
 /* blocks until every queued scan is done; *stats (optional) = the LAST scan's stats. */
 fdem_status fdem_mapper_wait(fdem_mapper* m, fdem_scan_stats* stats);
+/* Streaming form of the same call: submit() queues a scan and returns its ticket at once;
+ * collect() waits for THAT scan only and returns its stats.  Host inputs are copied on a
+ * separate stream into a double-buffered staging area, so `submit(k+1); collect(k);` overlaps
+ * the host->device copy of scan k+1 with the kernels of scan k.  Input buffers must stay
+ * valid until the scan's collect() returns; at most 8 scans may be outstanding. */
+fdem_status fdem_mapper_submit(fdem_mapper* m, const float* xyzw, const float* intensity,
+                               const uint8_t* rgb, size_t n, const double T_base_sensor[16],
+                               const double T_world_base[16], uint64_t* ticket);
+fdem_status fdem_mapper_collect(fdem_mapper* m, uint64_t ticket, fdem_scan_stats* stats);
 
 /* ElevationMapping::update(cloud, robot_position) (elevation_mapping.cpp:110-125): points
  * already in the map frame; var_z optional = cloud.covariance(i)(2,2) (null => cloud has no
@@ -270,6 +279,9 @@ fdem_status fdem_mapper_stage_times(fdem_mapper* m, double ms[FDEM_STAGE_COUNT],
  *   GLOBAL one CUB radix sort of the whole scan + warp-segmented reduce (kernels.cu) */
 enum { FDEM_CELL_SORT_TILE = 0, FDEM_CELL_SORT_GLOBAL = 1 };
 fdem_status fdem_mapper_set_cell_sort(fdem_mapper* m, int32_t mode);
+/* tuning aid: SM-clock timeline of CTA 0's first bucket in the last tile_estimate launch
+ * (out16[0..10] = phase boundaries in clock ticks since kernel entry, out16[15] = records) */
+fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* m, int64_t out16[16]);
 /* kernels launched through CUB (radix-sort passes) since the map was created */
 fdem_status fdem_mapper_library_launch_count(fdem_mapper* m, int64_t* launches);
 /* number of kernels THIS library launched since the handle was created (bench.py's

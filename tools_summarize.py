@@ -6,7 +6,7 @@ def bench(path):
     d = json.load(open(path))
     r = d["roofline"]
     print(f"{d['config']['workload']:18s} value {d['value']:8.0f} scans/s ({d['ms_per_step']*1e3:6.1f} us) "
-          f"{d['mpoints_per_s']:7.0f} Mpts/s | e2e {d['e2e']['value']:7.0f} | cpu {d['cpu_baseline']['value']:7.1f} "
+          f"{d['mpoints_per_s']:7.0f} Mpts/s | e2e {d['e2e']['value']:7.0f} (sync {d['e2e'].get('sync_value',0):.0f}, h2d {d['e2e'].get('pinned_h2d_gbs',0):.1f} GB/s) | cpu {d['cpu_baseline']['value']:7.1f} "
           f"({d['cpu_baseline']['ms_per_scan']:.2f} ms) | stages us "
           f"{ {k: round(v*1e3,1) for k,v in r['stage_ms'].items()} } | dom {r['kernel']} frac {r['frac']:.4f} "
           f"pipe {r['pipeline']['frac']:.4f} | launches {d['gpu_launches']}+{d['library_launches']} | {d['last_scan']}")
