@@ -179,6 +179,14 @@ def pose_for(wl, k):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, torchrun notices)
+    # write to fd 1 as well, so park fd 1 on stderr until the result is ready
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -199,7 +207,7 @@ def main():
     if args.impl == "reference":
         out = run_reference(args, wl, rank, world)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return 0
 
     args.warmup = max(args.warmup, 3)
@@ -208,7 +216,7 @@ def main():
     import fastdem_b200 as fd
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}), flush=True)
+        emit({"error": "no CUDA device: the hot path has no CPU fallback"})
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -255,6 +263,23 @@ def main():
             pin_scans.append(pc)
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+        if sharded:
+            # every rank needs the scan: rank 0 (the ingest rank) broadcasts it over NCCL/NVLink
+            # inside the timed step; the other ranks integrate out of their receive buffers
+            rx = dev_scans[0]
+
+            def submit_dev(kk):
+                c = dev_scans[kk % n_ring] if rank == 0 else rx
+                dist.broadcast(c.xyzw, src=0)
+                if has_i:
+                    dist.broadcast(c.intensity, src=0)
+                if has_c:
+                    dist.broadcast(c.color, src=0)
+                dem.integrate_async(c, *syn.pose(wl, base + kk))
+        else:
+            def submit_dev(kk):
+                dem.integrate_async(dev_scans[kk % n_ring], *syn.pose(wl, base + kk))
+
         def barrier():
             torch.cuda.synchronize(dev)
             if distributed:
@@ -264,7 +289,7 @@ def main():
         # ── warm-up (also sizes every scratch buffer) ──
         k = 0
         for _ in range(args.warmup):
-            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            submit_dev(k)
             k += 1
         dem.wait()
 
@@ -280,7 +305,7 @@ def main():
             if not args.no_flush:
                 flush_buf.fill_(i & 0xFF)
             ev[i][0].record(stream)
-            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            submit_dev(k)
             ev[i][1].record(stream)
             k += 1
         last = dem.wait()
@@ -297,7 +322,7 @@ def main():
         for i in range(min(args.steps, 64)):
             if not args.no_flush:
                 flush_buf.fill_(i & 0xFF)
-            dem.integrate_async(dev_scans[k % n_ring], *syn.pose(wl, base + k))
+            submit_dev(k)
             k += 1
         dem.wait()
         stage_ms, stage_scans = dem.stage_times()
@@ -313,29 +338,62 @@ def main():
         #    form submit(k+1); collect(k) lets the copy of the next scan overlap the kernels of
         #    the current one (double-buffered staging on a copy stream inside the library) ──
         e2e_steps = args.steps
-        for _ in range(3):
+        if sharded:
+            # host scan on the ingest rank -> its GPU -> NCCL broadcast -> every stripe integrates;
+            # the per-step result read is the stats of this rank's stripe
+            def e2e_step(kk):
+                if rank == 0:
+                    p = pin_scans[kk % n_ring]._pinned
+                    rx.xyzw.copy_(p["xyzw"], non_blocking=True)
+                    if has_i:
+                        rx.intensity.copy_(p["intensity"], non_blocking=True)
+                    if has_c:
+                        rx.color.copy_(p["rgb"], non_blocking=True)
+                dist.broadcast(rx.xyzw, src=0)
+                if has_i:
+                    dist.broadcast(rx.intensity, src=0)
+                if has_c:
+                    dist.broadcast(rx.color, src=0)
+                return dem.integrate_stats(rx, *syn.pose(wl, base + kk))
+            rx = fd.PointCloud(torch.empty_like(dev_scans[0].xyzw),
+                               None if not has_i else torch.empty_like(dev_scans[0].intensity),
+                               None if not has_c else torch.empty_like(dev_scans[0].color))
+            for _ in range(3):
+                e2e_step(k)
+                k += 1
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step(k)
+                k += 1
+            barrier()
+            e2e_s = e2e_sync_s = time.perf_counter() - t0
+        for _ in range(0 if sharded else 3):
             dem.integrate_stats(pin_scans[k % n_ring], *syn.pose(wl, base + k))
             k += 1
         barrier()
         t0 = time.perf_counter()
         prev = None
-        for _ in range(e2e_steps):
+        for _ in range(0 if sharded else e2e_steps):
             t = dem.submit(pin_scans[k % n_ring], *syn.pose(wl, base + k))
             k += 1
             if prev is not None:
                 dem.collect(prev)
             prev = t
-        dem.collect(prev)
+        if prev is not None:
+            dem.collect(prev)
         barrier()
-        e2e_s = time.perf_counter() - t0
+        if not sharded:
+            e2e_s = time.perf_counter() - t0
         # same thing fully synchronous (one scan in flight): integrate() per step
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(0 if sharded else e2e_steps):
             dem.integrate_stats(pin_scans[k % n_ring], *syn.pose(wl, base + k))
             k += 1
         barrier()
-        e2e_sync_s = time.perf_counter() - t0
+        if not sharded:
+            e2e_sync_s = time.perf_counter() - t0
         # context: what the PCIe link does for this scan size (pinned H2D, CUDA events)
         hb = pin_scans[0]._pinned["xyzw"]
         db_ = torch.empty_like(dev_scans[0].xyzw)
@@ -369,9 +427,14 @@ def main():
         dom_ms = timed[dominant]
         dom_bytes = per_stage_bytes.get(dominant, 0.0)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        try:  # measured DRAM bytes per launch of that kernel (one ncu --set full capture)
+            traffic = json.loads((REPO / "profiles" / "r1_traffic.json").read_text()).get(wl.name, {}).get(dominant)
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": dom_bytes,
             "kernel_ms": dom_ms,
             "stage_ms": stage_avg,
@@ -428,7 +491,7 @@ def main():
                                        "the reference path is single-threaded"},
             "last_scan": {"n_kept": int(last.n_kept), "n_cells": int(last.n_cells)},
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()

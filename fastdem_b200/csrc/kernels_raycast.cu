@@ -157,13 +157,28 @@ raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* 
     t_delta_c = 1e30f;
   }
   const int max_steps = nrows + ncols;
+  // The sensor cell is inside the map (precondition above) and the map is convex, so once
+  // the ray has left the map it never comes back: the reference keeps stepping (its cells
+  // fail the bounds test and are ignored); stopping there changes nothing but the work.
+  bool was_inside = false;
   for (int s = 0; s < max_steps; ++s) {
     if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
-      const int mr = (r + g.start[0]) % nrows;
-      const int mc = (c + g.start[1]) % ncols;
+      was_inside = true;
+      int mr = r + g.start[0];  // == (r + start) % size: both terms are in [0, size)
+      if (mr >= nrows) mr -= nrows;
+      int mc = c + g.start[1];
+      if (mc >= ncols) mc -= ncols;
       const float t_exit = fminf(t_max_r, t_max_c);
       const float height = sz + fminf(t_exit, 1.0f) * dz;
-      atomicMin(&p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr], enc_f32(height));
+      // Every ray starts in the sensor's cell, so the cells around it would take one atomic
+      // per ray.  A minimum only ever decreases: if the value already stored (even a stale,
+      // cached one — it can only be larger than the true current value) is <= mine, my
+      // update cannot change anything and the atomic is skipped.
+      uint32_t* slot = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
+      const uint32_t e = enc_f32(height);
+      if (e < *slot) atomicMin(slot, e);  // plain (L1-cacheable) load: staleness is safe here
+    } else if (was_inside) {
+      break;
     }
     if (t_max_r < t_max_c) {
       if (t_max_r >= 1.0f) break;

@@ -1,9 +1,21 @@
 """Row-stripe sharding of ONE global map over the ranks of a torch.distributed job
-(SURVEY.md §8e): rank g owns logical rows [g*R/G, (g+1)*R/G) of every layer.  integrate()
-needs no collective on the data path — after binning, a cell's update depends only on that
-cell's state and the scan's points in it — so every rank receives the full scan (broadcast
-from the ingest rank) and keeps only the keys whose row falls in its stripe."""
+(SURVEY.md §8e): rank g owns logical rows [g*R/G, (g+1)*R/G) of every layer.
+
+integrate() needs no collective on map data — after binning, a cell's update depends only on
+that cell's state and the scan's points in it — so every rank receives the scan (one
+broadcast from the ingest rank: NCCL over NVLink on GPUs, gloo in the CPU tests) and the
+binning kernel keeps only the keys whose row falls in the rank's stripe
+(fdem_map_create_stripe).  Collectives appear only where the path has a real exchange:
+gathering a layer, map-wide reductions (isEmpty), and the one-row halo exchange of stencil
+post-processing.
+
+The local engine is pluggable so the collective plumbing can be tested on CPU (gloo) with an
+oracle-backed engine; the product engine is the CUDA stripe map."""
 from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
 
 
 def stripe_bounds(rows: int, world: int, rank: int):
@@ -12,3 +24,218 @@ def stripe_bounds(rows: int, world: int, rank: int):
     r0 = rank * base + min(rank, extra)
     r1 = r0 + base + (1 if rank < extra else 0)
     return r0, r1
+
+
+def grid_rows(length: float, resolution: float) -> int:
+    """size = round(length / resolution) with the float32 arguments widened to double, as
+    ElevationMap::setGeometry does (elevation_map.hpp:112-116)."""
+    return int(round(float(np.float32(length)) / float(np.float32(resolution))))
+
+
+class CudaStripe:
+    """Product engine: this rank's stripe as a device-resident map + mapper."""
+
+    def __init__(self, width, height, resolution, cfg, r0, r1, device=0, stream=0):
+        from . import api
+        self.map = api.ElevationMap(width, height, resolution, "map", device=device, stream=stream,
+                                    row_stripe=(r0, r1))
+        self.dem = api.FastDEM(self.map, cfg)
+        self._api = api
+
+    def integrate(self, xyzw, intensity, rgb, Tbs, Twb):
+        cloud = self._api.PointCloud()
+        cloud.xyzw, cloud.intensity, cloud.color = xyzw, intensity, rgb
+        return self.dem.integrate_stats(cloud, Tbs, Twb)
+
+    def integrate_async(self, xyzw, intensity, rgb, Tbs, Twb):
+        cloud = self._api.PointCloud()
+        cloud.xyzw, cloud.intensity, cloud.color = xyzw, intensity, rgb
+        self.dem.integrate_async(cloud, Tbs, Twb)
+
+    def wait(self):
+        return self.dem.wait()
+
+    def get(self, name):
+        return self.map.get(name)
+
+    def exists(self, name):
+        return self.map.exists(name)
+
+    def is_empty(self):
+        return self.map.isEmpty()
+
+
+class ShardedGlobalMap:
+    """fastdem::ElevationMap + FastDEM (GLOBAL mode) striped over a process group."""
+
+    def __init__(self, width: float, height: float, resolution: float, cfg, *, group=None,
+                 device: Optional[int] = None, stream: int = 0,
+                 engine_factory: Optional[Callable] = None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if cfg.mode != 1:
+            raise ValueError("row-stripe sharding is for GLOBAL mapping (LOCAL maps follow the robot; "
+                             "run replicas instead)")
+        self.rows = grid_rows(width, resolution)
+        self.cols = grid_rows(height, resolution)
+        self.r0, self.r1 = stripe_bounds(self.rows, self.world, self.rank)
+        backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        self.on_gpu = backend == "nccl" or (backend == "none" and engine_factory is None)
+        self.comm_device = torch.device("cuda", device if device is not None else 0) if backend == "nccl" \
+            else torch.device("cpu")
+        if engine_factory is None:
+            self.engine = CudaStripe(width, height, resolution, cfg, self.r0, self.r1,
+                                     device=device if device is not None else 0, stream=stream)
+        else:
+            self.engine = engine_factory(width, height, resolution, cfg, self.r0, self.r1)
+        self._hdr = torch.zeros(40, dtype=torch.float64, device=self.comm_device)
+        self._bufs = {}
+
+    # ── scan distribution ──
+    def _buffer(self, key, shape, dtype):
+        b = self._bufs.get(key)
+        if b is None or b.shape[0] < shape[0]:
+            b = self.torch.empty(shape, dtype=dtype, device=self.comm_device)
+            self._bufs[key] = b
+        return b[:shape[0]]
+
+    def _to_comm(self, a, dtype):
+        t = a if self.torch.is_tensor(a) else self.torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=self.comm_device, dtype=dtype).contiguous()
+
+    def broadcast_scan(self, xyzw, intensity, rgb, Tbs, Twb, src: int = 0):
+        """One header broadcast + one broadcast per channel; every rank returns the scan in
+        the communication device's memory."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return xyzw, intensity, rgb, np.asarray(Tbs, np.float64), np.asarray(Twb, np.float64)
+        hdr = self._hdr
+        if self.rank == src:
+            n = int(xyzw.shape[0])
+            hdr[0], hdr[1], hdr[2] = n, 0 if intensity is None else 1, 0 if rgb is None else 1
+            hdr[8:24] = torch.from_numpy(np.asarray(Tbs, np.float64).reshape(16)).to(hdr.device)
+            hdr[24:40] = torch.from_numpy(np.asarray(Twb, np.float64).reshape(16)).to(hdr.device)
+        dist.broadcast(hdr, src=src, group=self.group)
+        h = hdr.cpu().numpy()
+        n, has_i, has_c = int(h[0]), bool(h[1]), bool(h[2])
+        Tbs, Twb = h[8:24].reshape(4, 4).copy(), h[24:40].reshape(4, 4).copy()
+        if self.rank == src:
+            px = self._to_comm(xyzw, torch.float32)
+            pi = self._to_comm(intensity, torch.float32) if has_i else None
+            pc = self._to_comm(rgb, torch.uint8) if has_c else None
+        else:
+            px = self._buffer("xyzw", (n, 4), torch.float32)
+            pi = self._buffer("intensity", (n,), torch.float32) if has_i else None
+            pc = self._buffer("rgb", (n, 3), torch.uint8) if has_c else None
+        dist.broadcast(px, src=src, group=self.group)
+        if has_i:
+            dist.broadcast(pi, src=src, group=self.group)
+        if has_c:
+            dist.broadcast(pc, src=src, group=self.group)
+        return px, pi, pc, Tbs, Twb
+
+    def _engine_inputs(self, px, pi, pc):
+        if self.on_gpu:
+            return px, pi, pc  # CUDA tensors (or host arrays at world 1) go straight to the C-ABI
+        conv = lambda t: None if t is None else (t.numpy() if self.torch.is_tensor(t) else t)
+        return conv(px), conv(pi), conv(pc)
+
+    # ── FastDEM::integrate on the sharded map ──
+    def integrate(self, xyzw=None, intensity=None, rgb=None, T_base_sensor=None, T_world_base=None,
+                  src: int = 0):
+        px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
+        a, b, c = self._engine_inputs(px, pi, pc)
+        return self.engine.integrate(a, b, c, Tbs, Twb)
+
+    def integrate_async(self, xyzw=None, intensity=None, rgb=None, T_base_sensor=None,
+                        T_world_base=None, src: int = 0):
+        px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
+        a, b, c = self._engine_inputs(px, pi, pc)
+        self._keep = (px, pi, pc)
+        self.engine.integrate_async(a, b, c, Tbs, Twb)
+
+    def wait(self):
+        return self.engine.wait()
+
+    # ── map-wide queries ──
+    def gather(self, name: str, dst: int = 0):
+        """The whole layer (rows x cols, Fortran order) on `dst`; None elsewhere."""
+        torch, dist = self.torch, self.dist
+        local = np.asarray(self.engine.get(name), dtype=np.float32)
+        if self.world == 1:
+            return np.asfortranarray(local)
+        # stripes differ by at most one row: pad to the largest and trim after the gather
+        max_rows = stripe_bounds(self.rows, self.world, 0)[1]
+        pad = np.full((max_rows, self.cols), np.nan, np.float32)
+        pad[: local.shape[0]] = local
+        t = torch.from_numpy(pad).to(self.comm_device)
+        out = [torch.empty_like(t) for _ in range(self.world)] if self.rank == dst else None
+        dist.gather(t, out, dst=dst, group=self.group)
+        if self.rank != dst:
+            return None
+        full = np.empty((self.rows, self.cols), np.float32, order="F")
+        for g, part in enumerate(out):
+            r0, r1 = stripe_bounds(self.rows, self.world, g)
+            full[r0:r1] = part.cpu().numpy()[: r1 - r0]
+        return full
+
+    def is_empty(self) -> bool:
+        """ElevationMap::isEmpty over all stripes (all-reduce of one flag)."""
+        flag = self.torch.tensor([1 if self.engine.is_empty() else 0], dtype=self.torch.int32,
+                                 device=self.comm_device)
+        if self.world > 1:
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(int(flag.item()))
+
+    def exchange_halo_rows(self, layer_rows_top: np.ndarray, layer_rows_bottom: np.ndarray):
+        """One boundary row to each neighbour stripe (3x3 stencils need exactly one): returns
+        (row above my first row, row below my last row), NaN rows at the map border."""
+        torch, dist = self.torch, self.dist
+        nan_row = np.full(self.cols, np.nan, np.float32)
+        if self.world == 1:
+            return nan_row, nan_row.copy()
+        up, down = self.rank - 1, self.rank + 1
+        send_top = torch.from_numpy(np.ascontiguousarray(layer_rows_top, np.float32)).to(self.comm_device)
+        send_bot = torch.from_numpy(np.ascontiguousarray(layer_rows_bottom, np.float32)).to(self.comm_device)
+        recv_above = torch.full((self.cols,), float("nan"), dtype=torch.float32, device=self.comm_device)
+        recv_below = torch.full((self.cols,), float("nan"), dtype=torch.float32, device=self.comm_device)
+        ops = []
+        if up >= 0:
+            ops += [dist.P2POp(dist.isend, send_top, up, self.group), dist.P2POp(dist.irecv, recv_above, up, self.group)]
+        if down < self.world:
+            ops += [dist.P2POp(dist.isend, send_bot, down, self.group), dist.P2POp(dist.irecv, recv_below, down, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return recv_above.cpu().numpy(), recv_below.cpu().numpy()
+
+    def inpaint(self, max_iterations: int = 3, min_valid_neighbors: int = 2):
+        """applyInpainting (fastdem/src/inpainting.cpp:21-67) on the sharded `elevation` layer →
+        `elevation_inpainted` stripes, one halo-row exchange per sweep.  Host-side stencil on the
+        stripe (post-processing, not the hot path); returns this rank's stripe."""
+        cur = np.asarray(self.engine.get("elevation"), np.float32).copy()
+        R = cur.shape[0]
+        for _ in range(max_iterations):
+            above, below = self.exchange_halo_rows(cur[0], cur[-1])
+            padded = np.full((R + 2, self.cols + 2), np.nan, np.float32)
+            padded[1:-1, 1:-1] = cur
+            padded[0, 1:-1] = above
+            padded[-1, 1:-1] = below
+            total = np.zeros((R, self.cols), np.float32)
+            count = np.zeros((R, self.cols), np.int32)
+            for dr in (-1, 0, 1):          # the oracle's neighbour order: dr outer, dc inner
+                for dc in (-1, 0, 1):
+                    if dr == 0 and dc == 0:
+                        continue
+                    nb = padded[1 + dr: 1 + dr + R, 1 + dc: 1 + dc + self.cols]
+                    ok = np.isfinite(nb)
+                    total = np.where(ok, total + np.where(ok, nb, np.float32(0)), total).astype(np.float32)
+                    count += ok
+            fill = np.isnan(cur) & (count >= min_valid_neighbors)
+            nxt = cur.copy()
+            nxt[fill] = (total[fill] / count[fill].astype(np.float32)).astype(np.float32)
+            cur = nxt
+        return cur

@@ -1,0 +1,118 @@
+"""CPU, world_size 2, gloo: the collective plumbing of the row-stripe sharded global map
+(scan broadcast, layer gather, isEmpty all-reduce, halo-row exchange for the inpainting
+stencil) with an oracle-backed local engine.  The CUDA stripe engine itself is covered by
+tests/test_gpu_stripes.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_binding as ob
+from fastdem_b200 import capi, sharded
+from fastdem_b200 import synthetic as syn
+
+
+def test_stripe_bounds_partition():
+    for rows in (1, 7, 20, 8000, 8001):
+        for world in (1, 2, 3, 4, 8):
+            if world > rows:
+                continue
+            spans = [sharded.stripe_bounds(rows, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == rows
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert sharded.grid_rows(400.0, 0.05) == 8000 and sharded.grid_rows(10.0, 0.5) == 20
+
+
+class OracleStripe:
+    """Local engine for the CPU tests: the full map on the oracle, exposing only this rank's rows."""
+
+    def __init__(self, width, height, resolution, cfg, r0, r1):
+        self.map = ob.OracleMap(width, height, resolution)
+        self.dem = ob.OracleFastDEM(self.map, cfg)
+        self.r0, self.r1 = r0, r1
+
+    def integrate(self, xyzw, intensity, rgb, Tbs, Twb):
+        ok, st, _ = self.dem.integrate(xyzw, Tbs, Twb, intensity, rgb)
+        return st
+
+    def get(self, name):
+        return self.map.get(name)[self.r0:self.r1]
+
+    def exists(self, name):
+        return self.map.exists(name)
+
+    def is_empty(self):
+        return bool(np.isnan(self.get("elevation")).all())
+
+
+def _global_cfg():
+    wl = syn.WORKLOADS["tiny"]
+    cfg = wl.config()
+    cfg.mode = capi.MODE_GLOBAL
+    return wl, cfg
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl, cfg = _global_cfg()
+        sm = sharded.ShardedGlobalMap(wl.map_width, wl.map_height, wl.resolution, cfg,
+                                      engine_factory=OracleStripe)
+        assert (sm.r0, sm.r1) == sharded.stripe_bounds(100, world, rank)
+        assert sm.is_empty()
+        for k in range(4):
+            if rank == 0:   # the ingest rank has the scan; the others receive it
+                s = syn.make_scan(wl, k)
+                st = sm.integrate(s["xyzw"], s["intensity"], s["rgb"], s["T_base_sensor"], s["T_world_base"], src=0)
+            else:
+                st = sm.integrate(src=0)
+            assert st.integrated == 1
+        assert not sm.is_empty()
+        full = {name: sm.gather(name, dst=0) for name in ("elevation", "n_points", "variance", "intensity")}
+        inp = sm.inpaint(3, 2)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(inp, parts, dst=0)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "result.npz"), inpainted=np.concatenate(parts, axis=0), **full)
+        else:
+            assert all(v is None for v in full.values())
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_sharded_map_two_ranks_gloo(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "result.npz")
+    # single-process truth
+    wl, cfg = _global_cfg()
+    m = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    d = ob.OracleFastDEM(m, cfg)
+    for k in range(4):
+        s = syn.make_scan(wl, k)
+        d.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], s["rgb"])
+    for name in ("elevation", "n_points", "variance", "intensity"):
+        want = m.get(name)
+        assert np.array_equal(np.isnan(got[name]), np.isnan(want)), name
+        assert np.array_equal(np.nan_to_num(got[name]), np.nan_to_num(want)), name
+    m.inpaint(3, 2, False)
+    want = m.get("elevation_inpainted")
+    assert np.array_equal(np.isnan(got["inpainted"]), np.isnan(want))
+    assert np.allclose(np.nan_to_num(got["inpainted"]), np.nan_to_num(want), rtol=1e-6, atol=0)
+    assert np.isfinite(want).sum() > np.isfinite(m.get("elevation")).sum()  # holes were filled
