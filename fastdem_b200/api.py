@@ -158,6 +158,8 @@ class PointCloud:
 
 def _iso(T) -> np.ndarray:
     """Eigen::Isometry3d -> column-major double[16]."""
+    if isinstance(T, np.ndarray) and T.shape == (16,) and T.dtype == np.float64 and T.flags.c_contiguous:
+        return T  # already column-major double[16] (what _iso returns): hot-loop fast path
     M = np.asarray(T, dtype=np.float64)
     if M.shape != (4, 4):
         raise ValueError("transform must be 4x4")
@@ -581,6 +583,12 @@ class FastDEM:
         xyz = np.empty((max(nc.value, 1), 3), np.float32)
         check(self._lib.fdem_mapper_last_rasterized(self._h, xyz.ctypes.data, C.byref(nc)))
         return PointCloud(xyz[:nc.value], frame_id=self._map.getFrameId())
+
+    def debug_cta_times(self):
+        out = (C.c_uint64 * 1024)()
+        check(self._lib.fdem_mapper_debug_cta_times(self._h, out))
+        a = np.array(out, dtype=np.uint64).reshape(512, 2)
+        return a
 
     def debug_phase_clocks(self):
         out = (C.c_int64 * 16)()

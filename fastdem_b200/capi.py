@@ -118,6 +118,7 @@ SIGNATURES = {
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),
     "fdem_mapper_set_cell_sort": (_ST, [_P, C.c_int32]),
     "fdem_mapper_debug_phase_clocks": (_ST, [_P, C.POINTER(C.c_int64)]),
+    "fdem_mapper_debug_cta_times": (_ST, [_P, C.POINTER(C.c_uint64)]),
     "fdem_mapper_stage_times": (_ST, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

@@ -1499,6 +1499,15 @@ fdem_status fdem_mapper_last_rasterized(fdem_mapper* mp, float* xyz, int64_t* n_
   return FDEM_OK;
 }
 
+fdem_status fdem_mapper_debug_cta_times(fdem_mapper* mp, uint64_t* out1024) {
+  FDEM_REQUIRE(mp && out1024, "null argument");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  FDEM_CUDA_TRY(static_cast<cudaError_t>(
+      tile_estimate_debug_cta_ns(reinterpret_cast<unsigned long long*>(out1024))));
+  return FDEM_OK;
+}
+
 fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* mp, int64_t* out16) {
   FDEM_REQUIRE(mp && out16, "null argument");
   DeviceGuard dg(mp->map->device);

@@ -203,7 +203,8 @@ void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounte
 void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
                           DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
                           LaunchCounter& lc);
-int tile_estimate_debug_clocks(long long* out16);  // CTA 0 phase clocks of the last K3t launch
+int tile_estimate_debug_clocks(long long* out16);
+int tile_estimate_debug_cta_ns(unsigned long long* out1024);  // entry/exit ns of the first 512 CTAs  // CTA 0 phase clocks of the last K3t launch
 int tile_estimate_configure();  // one-time cudaFuncSetAttribute (dynamic smem); returns cudaError_t
 void launch_move_only(const DeviceState* st_in, DeviceState* st_out, double x, double y,
                       int clear_policy, const LayerTable& lt, uint32_t* moved_flag, cudaStream_t s,

@@ -143,6 +143,13 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
 // phase timeline of CTA 0's first bucket (SM clock ticks since kernel entry), for tuning:
 // read back through fdem_mapper_debug_phase_clocks().  One thread, a dozen clock reads.
 __device__ long long g_k3t_clocks[16];
+// wall-clock (globaltimer, ns) entry / exit of every CTA of the last launch (first 512 CTAs)
+__device__ unsigned long long g_k3t_cta_ns[2 * 512];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define K3T_MARK(i) do { if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[i] = clock64() - t_entry; } while (0)
 
 // ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
@@ -178,6 +185,7 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   const int warp = tid >> 5;
   const long long t_entry = clock64();
   bool first_job = true;
+  if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x] = globaltimer_ns();
 
   // prologue that needs nothing from the scatter kernel: overlaps its tail under PDL
   if (tid == 0) mbar_init(&S.mbar, 1);
@@ -418,9 +426,14 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
     }
   }
   K3T_MARK(10);  // kernel exit of CTA 0
+  if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x + 1] = globaltimer_ns();
 }
 
 }  // namespace
+
+int tile_estimate_debug_cta_ns(unsigned long long* out1024) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out1024, g_k3t_cta_ns, sizeof(unsigned long long) * 1024));
+}
 
 int tile_estimate_debug_clocks(long long* out16) {
   return static_cast<int>(cudaMemcpyFromSymbol(out16, g_k3t_clocks, sizeof(long long) * 16));

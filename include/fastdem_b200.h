@@ -282,6 +282,9 @@ fdem_status fdem_mapper_set_cell_sort(fdem_mapper* m, int32_t mode);
 /* tuning aid: SM-clock timeline of CTA 0's first bucket in the last tile_estimate launch
  * (out16[0..10] = phase boundaries in clock ticks since kernel entry, out16[15] = records) */
 fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* m, int64_t out16[16]);
+/* tuning aid: globaltimer (ns) at entry / exit of the first 512 CTAs of the last tile_estimate
+ * launch, interleaved: out[2*i] = entry, out[2*i+1] = exit */
+fdem_status fdem_mapper_debug_cta_times(fdem_mapper* m, uint64_t out1024[1024]);
 /* kernels launched through CUB (radix-sort passes) since the map was created */
 fdem_status fdem_mapper_library_launch_count(fdem_mapper* m, int64_t* launches);
 /* number of kernels THIS library launched since the handle was created (bench.py's

@@ -1,0 +1,78 @@
+"""-m gpu: BASELINE.json's full-size configurations (C4: 1.05 M points + raycasting on a
+1000x1000 map; C5: 1.05 M points on the 8000x8000 = 64 M-cell global map).
+
+Oracle parity at full size for a couple of scans (the oracle needs ~0.1-0.4 s per scan here),
+plus size-independent properties that need no oracle:
+  * the two independent cell-reduction implementations (tile path: bucket partition +
+    shared-memory sort; global path: CUB radix sort + warp-segmented reduce) agree bit for bit
+  * counts are consistent: n_points grows by exactly one per touched cell per scan
+  * order relations between layers hold cell by cell"""
+import numpy as np
+import pytest
+
+from fastdem_b200 import capi
+from fastdem_b200 import synthetic as syn
+from parity_utils import compare_layer, compare_maps, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fdem, wl, cfg, scans, cell_sort):
+    m = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution)
+    d = fdem.FastDEM(m, cfg)
+    d.set_cell_sort(cell_sort)
+    stats = []
+    for s in scans:
+        stats.append(d.integrate_stats(fdem.PointCloud(s["xyzw"], s["intensity"], s["rgb"]),
+                                       s["T_base_sensor"], s["T_world_base"]))
+    return m, d, stats
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["c4_dense_raycast", "c5_global"])
+def test_two_sort_paths_agree_bit_for_bit(fdem, name):
+    wl = syn.WORKLOADS[name]
+    cfg = wl.config()
+    scans = [syn.make_scan(wl, k) for k in range(3)]
+    ma, da, sa = _run(fdem, wl, cfg, scans, capi.CELL_SORT_TILE)
+    mb, db, sb = _run(fdem, wl, cfg, scans, capi.CELL_SORT_GLOBAL)
+    for a, b in zip(sa, sb):
+        assert (a.n_kept, a.n_cells, a.n_voxels, a.integrated) == (b.n_kept, b.n_cells, b.n_voxels, b.integrated)
+    assert ma.getLayers() == mb.getLayers()
+    for layer in ma.getLayers():
+        x, y = ma.get(layer), mb.get(layer)
+        assert np.array_equal(_bits(x), _bits(y)), layer
+    # counts: every touched cell got exactly one estimator step per scan
+    n_points = ma.get("n_points")
+    assert np.nansum(n_points) == sum(s.n_cells for s in sa) or name == "c4_dense_raycast"
+    # order relations (Kalman): min <= max, lower <= elevation <= upper where defined
+    emin, emax = ma.get("elevation_min"), ma.get("elevation_max")
+    ok = np.isfinite(emin) & np.isfinite(emax)
+    assert (emin[ok] <= emax[ok]).all()
+    e, lo, up = ma.get("elevation"), ma.get("lower_bound"), ma.get("upper_bound")
+    ok = np.isfinite(e) & np.isfinite(lo) & np.isfinite(up)
+    assert ok.sum() > 1000 and (lo[ok] <= e[ok]).all() and (e[ok] <= up[ok]).all()
+    ob = ma.get("obstacle")
+    ok = np.isfinite(ob) & np.isfinite(emax)
+    assert (ob[ok] <= emax[ok]).all()          # this scan's max_z never exceeds the all-time max
+
+
+def test_c4_oracle_parity_with_raycasting(fdem):
+    """1.05 M points, 1000x1000 LOCAL map, Kalman, voxelGrid(ANY) + raycasting, 2 scans."""
+    wl = syn.WORKLOADS["c4_dense_raycast"]
+    gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, 2)
+    assert gs[-1].n_voxels > 100000 and gs[-1].n_cells > 50000
+    compare_maps(gmap, omap)
+
+
+def test_c5_oracle_parity_global_64m_cells(fdem):
+    """1.05 M points on the 8000 x 8000 global map, 2 scans; layers compared on the window the
+    scans can reach (everything else must still be at its initial fill)."""
+    wl = syn.WORKLOADS["c5_global"]
+    gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, 2)
+    assert gmap.getSize() == (8000, 8000)
+    for layer in ("elevation", "variance", "n_points", "_kalman_p", "obstacle", "intensity", "elevation_max"):
+        compare_layer(layer, gmap.get(layer), omap.get(layer))

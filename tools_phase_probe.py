@@ -13,7 +13,11 @@ for wname in ["c2_lidar64_local","c3_rgbd_p2","c1_vlp16_local"]:
         c=fd.PointCloud(torch.from_numpy(s['xyzw']).cuda(), None if s['intensity'] is None else torch.from_numpy(s['intensity']).cuda(), None if s['rgb'] is None else torch.from_numpy(s['rgb']).cuda())
         flush.fill_(k); torch.cuda.synchronize()
         d.integrate_stats(c,*syn.pose(wl,k))
-        if k>=4: rows.append(d.debug_phase_clocks())
+        if k>=4:
+            rows.append(d.debug_phase_clocks())
+            ct=d.debug_cta_times().astype(np.int64); ct=ct[ct[:,0]>0]
+            t0=ct[:,0].min(); starts=(ct[:,0]-t0)/1e3; ends=(ct[:,1]-t0)/1e3; dur=ends-starts
+            if k==11: print(wname,'CTAs',len(ct),'span %.1f us'%ends.max(),'start p50/p90/max %.1f/%.1f/%.1f'%(np.percentile(starts,50),np.percentile(starts,90),starts.max()),'dur p50/p90/max %.1f/%.1f/%.1f'%(np.percentile(dur,50),np.percentile(dur,90),dur.max()))
     a=np.array(rows,dtype=np.float64)
     med=np.median(a,axis=0)
     print(wname,'records in CTA0 bucket (median)',med[15])
