@@ -78,12 +78,20 @@ class ClockSampler:
 
         def pump():
             for line in self.proc.stdout:
-                self.rows.append(line.strip())
+                self.rows.append((time.perf_counter(), line.strip()))
 
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def wait_first(self, timeout_s=5.0):
+        """nvidia-smi needs a few hundred ms before its first row; wait for it."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+
+    def stop(self, region=None):
+        """region = (t0, t1) perf_counter bounds of the timed steps: rows inside it are counted
+        separately from rows taken while the same load kept running around it."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,10 +101,13 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        in_region = 0
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
+            if region is not None and region[0] <= ts <= region[1] + 0.1:
+                in_region += 1
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
@@ -109,7 +120,11 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": in_region,
+                "how": "nvidia-smi -lms 100 started before warm-up and kept running while the same "
+                       "step loop continues for >=1 s after the timed steps (the timed region "
+                       "itself can be shorter than one sampling period)",
+                "reasons": sorted(reasons)}
 
 
 def algorithmic_bytes(wl, n_points, stats_list, has_i, has_c, p2):
@@ -189,8 +204,8 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_lidar64_local")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
@@ -312,6 +327,8 @@ def main():
             torch.cuda.synchronize(dev)
 
         # ── warm-up (also sizes every scratch buffer) ──
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         k = 0
         for _ in range(args.warmup):
             submit_dev(k)
@@ -319,15 +336,14 @@ def main():
         dem.wait()
 
         # ── timed region: device-resident inputs, CUDA events on the kernels' stream ──
+        sampler.wait_first()
         l0, lib0 = dem.launch_count(), dem.library_launch_count()
-        sampler = ClockSampler(local_rank)
         stats_ring = []
         if args.l2 == "flush":
             # everything cold: 256 MiB fill before each step, one event pair per step
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                   for _ in range(args.steps)]
             barrier()
-            sampler.start()
             t_cpu0 = time.perf_counter()
             for i in range(args.steps):
                 flush_buf.fill_(i & 0xFF)
@@ -344,7 +360,6 @@ def main():
             # >126 MB of other scans read since its last use
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
-            sampler.start()
             t_cpu0 = time.perf_counter()
             e0.record(stream)
             for i in range(args.steps):
@@ -355,9 +370,26 @@ def main():
             last = dem.wait()
             barrier()
             total_ms = float(e0.elapsed_time(e1))
-        clocks = sampler.stop()
+        t_region = (t_cpu0, time.perf_counter())
         launches = dem.launch_count() - l0
         lib_launches = dem.library_launch_count() - lib0
+        # keep the identical load running until nvidia-smi has seen >= 1 s of it (same step
+        # count on every rank: the sharded mode broadcasts inside each step)
+        per_step_s = max(total_ms * 1e-3 / max(args.steps, 1), 1e-6)
+        extra = int(min(200000, max(0.0, 1.2 - (t_region[1] - t_region[0])) / per_step_s))
+        if distributed:
+            t_extra = torch.tensor([extra], device=dev, dtype=torch.int64)
+            dist.all_reduce(t_extra, op=dist.ReduceOp.MAX)
+            extra = int(t_extra.item())
+        for i in range(extra):
+            if args.l2 == "flush":
+                flush_buf.fill_(i & 0xFF)
+            submit_dev(k)
+            k += 1
+            if (i & 255) == 255:
+                dem.wait()
+        dem.wait()
+        clocks = sampler.stop(t_region)
 
         # ── stage attribution pass (separate from the timed region: bracketing every stage
         #    with events costs ~2.7 us per event and forces one launch per kernel) ──

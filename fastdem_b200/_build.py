@@ -77,7 +77,7 @@ def build_oracle(force: bool = False) -> Path:
     """Test infrastructure: the CPU oracle (oracle/).  Building the checker is not using it."""
     odir = REPO / "oracle"
     lib = odir / "libfdem_oracle.so"
-    if force or _stale(lib, [odir / "fdem_oracle.hpp", odir / "fdem_oracle_capi.cpp", odir / "Makefile"]):
+    if force or _stale(lib, [odir / "fdem_oracle.hpp", odir / "fdem_oracle_capi.cpp", odir / "fdem_oracle_io.cpp", odir / "Makefile"]):
         r = subprocess.run(["make", "-C", str(odir)] + (["-B"] if force else []),
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         if r.returncode != 0:

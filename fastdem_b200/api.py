@@ -156,6 +156,89 @@ class PointCloud:
         self._timestamp = ns
 
 
+# sensor_msgs/PointField datatypes (nanopcl/bridge/ros/impl.hpp:22-31)
+PF_INT8, PF_UINT8, PF_INT16, PF_UINT16, PF_INT32, PF_UINT32, PF_FLOAT32, PF_FLOAT64 = 1, 2, 3, 4, 5, 6, 7, 8
+
+
+class PointCloud2:
+    """A sensor_msgs/PointCloud2 message body: `data` (bytes / uint8 numpy / uint8 torch CUDA
+    tensor), width x height points of `point_step` bytes, `fields` = [(name, offset, datatype)].
+    FastDEM.integrate(msg, ...) == integrate(nanopcl::from(msg), ...) with the unpacking done
+    on the device."""
+
+    def __init__(self, data, width: int, height: int, point_step: int, fields, frame_id: str = "",
+                 timestamp: int = 0):
+        self.data = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else data
+        self.width, self.height, self.point_step = int(width), int(height), int(point_step)
+        self.fields = list(fields)
+        self._frame_id, self._timestamp = frame_id, timestamp
+
+    def size(self) -> int:
+        return self.width * self.height
+
+    def empty(self) -> bool:
+        return self.size() == 0
+
+    def frameId(self) -> str:
+        return self._frame_id
+
+    def timestamp(self) -> int:
+        return self._timestamp
+
+    def layout(self) -> capi.FdemPointCloud2Layout:
+        """FieldOffsets::parse (nanopcl/bridge/ros/impl.hpp:66-104)."""
+        lo = capi.FdemPointCloud2Layout(self.point_step, -1, -1, -1, -1, 0, -1)
+        for name, offset, datatype in self.fields:
+            if name == "x":
+                lo.off_x = offset
+            elif name == "y":
+                lo.off_y = offset
+            elif name == "z":
+                lo.off_z = offset
+            elif name == "intensity":
+                lo.off_intensity, lo.intensity_type = offset, datatype
+            elif name in ("rgb", "rgba"):
+                lo.off_rgb = offset
+        return lo
+
+    @staticmethod
+    def from_arrays(xyz, intensity=None, rgb=None, intensity_type=PF_FLOAT32, pad: int = 0):
+        """Pack arrays the way ROS drivers do (x, y, z, [intensity], [rgb], padding)."""
+        xyz = np.asarray(xyz, np.float32)
+        n = xyz.shape[0]
+        fields = [("x", 0, PF_FLOAT32), ("y", 4, PF_FLOAT32), ("z", 8, PF_FLOAT32)]
+        dt = [("x", "<f4"), ("y", "<f4"), ("z", "<f4")]
+        off = 12
+        if intensity is not None:
+            np_t = {PF_UINT8: "u1", PF_UINT16: "<u2", PF_FLOAT32: "<f4", PF_FLOAT64: "<f8"}[intensity_type]
+            align = 4 if intensity_type in (PF_FLOAT32, PF_FLOAT64) else np.dtype(np_t).itemsize
+            while off % align:
+                dt.append((f"_p{off}", "u1"))
+                off += 1
+            fields.append(("intensity", off, intensity_type))
+            dt.append(("intensity", np_t))
+            off += np.dtype(np_t).itemsize
+        if rgb is not None:
+            while off % 4:
+                dt.append((f"_p{off}", "u1"))
+                off += 1
+            fields.append(("rgb", off, PF_FLOAT32))
+            dt.append(("rgb", "<u4"))
+            off += 4
+        step = -(-(off + pad) // 4) * 4
+        while off < step:
+            dt.append((f"_p{off}", "u1"))
+            off += 1
+        a = np.zeros(n, dtype=np.dtype(dt))
+        a["x"], a["y"], a["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        if intensity is not None:
+            a["intensity"] = np.asarray(intensity).astype(a.dtype["intensity"])
+        if rgb is not None:
+            c = np.asarray(rgb, np.uint32)
+            a["rgb"] = (c[:, 0] << 16) | (c[:, 1] << 8) | c[:, 2]
+        return PointCloud2(a.view(np.uint8).reshape(-1), n, 1, step, fields)
+
+
 def _iso(T) -> np.ndarray:
     """Eigen::Isometry3d -> column-major double[16]."""
     if isinstance(T, np.ndarray) and T.shape == (16,) and T.dtype == np.float64 and T.flags.c_contiguous:
@@ -486,8 +569,21 @@ class FastDEM:
             T_world_base = self._odometry.getPoseAt(cloud.timestamp())
             if T_world_base is None:
                 return False
+        if isinstance(cloud, PointCloud2):
+            return bool(self.integrate_pointcloud2(cloud, T_base_sensor, T_world_base).integrated)
         stats = self.integrate_stats(cloud, T_base_sensor, T_world_base)
         return bool(stats.integrated)
+
+    def integrate_pointcloud2(self, msg: "PointCloud2", T_base_sensor, T_world_base) -> FdemScanStats:
+        """integrate(nanopcl::from(msg), ...): the message body goes to the device as it is."""
+        p, keep, _ = _ptr(msg.data, np.uint8)
+        lo = msg.layout()
+        Tbs, Twb = _iso(T_base_sensor), _iso(T_world_base)
+        stats = FdemScanStats()
+        check(self._lib.fdem_mapper_integrate_pointcloud2(
+            self._h, p, msg.size(), C.byref(lo), Tbs.ctypes.data_as(C.POINTER(C.c_double)),
+            Twb.ctypes.data_as(C.POINTER(C.c_double)), C.byref(stats)))
+        return stats
 
     def _channels(self, cloud: PointCloud):
         n = cloud.size()
@@ -663,3 +759,10 @@ def applyInpainting(map: ElevationMap, max_iterations: int = 3, min_valid_neighb
                     inplace: bool = False) -> None:
     lib = capi.load_library()
     check(lib.fdem_inpaint(map.handle, max_iterations, min_valid_neighbors, 1 if inplace else 0))
+
+
+def applySpatialSmoothing(map: ElevationMap, layer_name: str, kernel_size: int = 3,
+                          min_valid_neighbors: int = 5) -> None:
+    """fastdem::applySpatialSmoothing (postprocess/spatial_smoothing.hpp:38-67)."""
+    lib = capi.load_library()
+    check(lib.fdem_spatial_smoothing(map.handle, layer_name.encode(), kernel_size, min_valid_neighbors))

@@ -51,6 +51,12 @@ class FdemScanStats(C.Structure):
                 ("n_voxels", C.c_int64), ("integrated", C.c_int32), ("_pad", C.c_int32)]
 
 
+class FdemPointCloud2Layout(C.Structure):
+    _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_int32), ("off_y", C.c_int32),
+                ("off_z", C.c_int32), ("off_intensity", C.c_int32), ("intensity_type", C.c_int32),
+                ("off_rgb", C.c_int32)]
+
+
 class FdemGeometry(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("resolution", C.c_double),
                 ("length", C.c_double * 2), ("position", C.c_double * 2),
@@ -101,6 +107,8 @@ SIGNATURES = {
     "fdem_mapper_integrate": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p,
                                     C.POINTER(FdemScanStats)]),
     "fdem_mapper_integrate_async": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p]),
+    "fdem_mapper_integrate_pointcloud2": (_ST, [_P, _u8p, C.c_size_t, C.POINTER(FdemPointCloud2Layout),
+                                                _f64p, _f64p, C.POINTER(FdemScanStats)]),
     "fdem_mapper_wait": (_ST, [_P, C.POINTER(FdemScanStats)]),
     "fdem_mapper_submit": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p, C.POINTER(C.c_uint64)]),
     "fdem_mapper_collect": (_ST, [_P, C.c_uint64, C.POINTER(FdemScanStats)]),
@@ -113,6 +121,7 @@ SIGNATURES = {
     "fdem_raycast": (_ST, [_P, _f32p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(FdemConfig)]),
     "fdem_voxel_grid_any": (_ST, [_P, _f32p, C.c_size_t, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]),
     "fdem_inpaint": (_ST, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fdem_spatial_smoothing": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),

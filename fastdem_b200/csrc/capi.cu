@@ -140,6 +140,8 @@ struct fdem_mapper {
   float* d_in_intensity[kStageRing] = {};
   uint8_t* d_in_rgb[kStageRing] = {};
   float* d_in_aux[kStageRing] = {};  // cov9 (N x 9) or var_z (N)
+  uint8_t* d_in_raw[kStageRing] = {};  // PointCloud2 message bodies
+  size_t raw_cap = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[kStageRing] = {};
   uint64_t last_ticket = 0;
@@ -152,6 +154,7 @@ struct fdem_mapper {
   uint32_t* d_counters = nullptr;
   fdem_scan_stats last{};
   uint32_t last_n = 0;
+  bool last_raw = false;
   bool last_had_work = false;
   bool pending = false;  // async scans queued since the last wait
   // tile path (2-level sort-by-cell); global CUB sort kept as the alternative path
@@ -334,6 +337,8 @@ void free_scratch(fdem_mapper* mp) {
   cudaFree(mp->d_svkeys);
   cudaFree(mp->d_sel);
   cudaFree(mp->d_sort_temp);
+  for (int i = 0; i < kStageRing; ++i) { cudaFree(mp->d_in_raw[i]); mp->d_in_raw[i] = nullptr; }
+  mp->raw_cap = 0;
   cudaFree(mp->tb.records);
   mp->tb.records = nullptr;
   mp->d_pm = nullptr; mp->d_keys = mp->d_vals = nullptr;
@@ -478,6 +483,8 @@ struct ScanInputs {
   const double* Tbs;
   const double* Twb;
   double robot_x, robot_y;
+  const uint8_t* raw = nullptr;                    // PointCloud2 body (xyzw etc. null then)
+  const fdem_pointcloud2_layout* layout = nullptr;
 };
 
 fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
@@ -504,8 +511,8 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   mark(FDEM_STAGE_H2D);
   // layers the cloud's channels need (updateIntensity / updateColor add them lazily,
   // elevation_mapping.cpp:155,169)
-  if (in.intensity) FDEM_TRY(ensure_layer(m, "intensity", kNaN));
-  if (in.rgb) FDEM_TRY(ensure_layer(m, "color", kNaN));
+  if (in.intensity || (in.layout && in.layout->off_intensity >= 0)) FDEM_TRY(ensure_layer(m, "intensity", kNaN));
+  if (in.rgb || (in.layout && in.layout->off_rgb >= 0)) FDEM_TRY(ensure_layer(m, "color", kNaN));
 
   PreprocessParams pp{};
   // Inputs already on the device are used in place.  Host inputs are copied into staging
@@ -530,9 +537,35 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
     return FDEM_OK;
   };
   const void *xyzw_v = nullptr, *inten_v = nullptr, *rgb_v = nullptr, *aux_v = nullptr;
+  const void* raw_v = nullptr;
+  if (in.raw) {
+    const fdem_pointcloud2_layout& lo = *in.layout;
+    const size_t bytes = static_cast<size_t>(n) * lo.point_step;
+    if (!is_device_pointer(in.raw) && mp->raw_cap < bytes) {
+      FDEM_CUDA_TRY(cudaStreamSynchronize(s));
+      FDEM_CUDA_TRY(cudaStreamSynchronize(mp->copy_stream));
+      for (int i = 0; i < kStageRing; ++i) {
+        cudaFree(mp->d_in_raw[i]);
+        mp->d_in_raw[i] = nullptr;
+        FDEM_CUDA_TRY(cudaMalloc(&mp->d_in_raw[i], bytes + 16));
+      }
+      mp->raw_cap = bytes;
+    }
+    FDEM_TRY(stage_in(in.raw, mp->d_in_raw[slot], bytes, &raw_v));
+    FDEM_REQUIRE((reinterpret_cast<uintptr_t>(raw_v) & 3) == 0, "PointCloud2 data must be 4-byte aligned");
+    pp.raw = static_cast<const uint8_t*>(raw_v);
+    pp.point_step = lo.point_step;
+    pp.off_x = lo.off_x; pp.off_y = lo.off_y; pp.off_z = lo.off_z;
+    pp.off_intensity = lo.off_intensity; pp.intensity_type = lo.intensity_type; pp.off_rgb = lo.off_rgb;
+    // K1 unpacks the channels into the staging slot's SoA buffers for the later kernels
+    if (lo.off_intensity >= 0) { pp.out_intensity = mp->d_in_intensity[slot]; inten_v = pp.out_intensity; }
+    if (lo.off_rgb >= 0) { pp.out_rgb = mp->d_in_rgb[slot]; rgb_v = pp.out_rgb; }
+  }
   FDEM_TRY(stage_in(in.xyzw, mp->d_in_xyzw[slot], static_cast<size_t>(n) * 16, &xyzw_v));
-  FDEM_TRY(stage_in(in.intensity, mp->d_in_intensity[slot], static_cast<size_t>(n) * 4, &inten_v));
-  FDEM_TRY(stage_in(in.rgb, mp->d_in_rgb[slot], static_cast<size_t>(n) * 3, &rgb_v));
+  if (!in.raw) {
+    FDEM_TRY(stage_in(in.intensity, mp->d_in_intensity[slot], static_cast<size_t>(n) * 4, &inten_v));
+    FDEM_TRY(stage_in(in.rgb, mp->d_in_rgb[slot], static_cast<size_t>(n) * 3, &rgb_v));
+  }
   if (in.cov9) FDEM_TRY(stage_in(in.cov9, mp->d_in_aux[slot], static_cast<size_t>(n) * 36, &aux_v));
   if (in.var_z) FDEM_TRY(stage_in(in.var_z, mp->d_in_aux[slot], static_cast<size_t>(n) * 4, &aux_v));
   if (staged && overlap) {
@@ -729,6 +762,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   mp->last_ticket = ticket;
   m->geom_stale = true;
   mp->last_n = n;
+  mp->last_raw = in.raw != nullptr;
   mp->last_had_work = true;
   mp->pending = true;
   return FDEM_OK;
@@ -828,7 +862,7 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
     const ScanResult& r = m->h_result[mp->last_ticket % kResultRing];
     m->geom = r.state.geom;
     m->geom_stale = false;
-    mp->last.n_input = mp->last_n;
+    mp->last.n_input = mp->last_raw ? r.counters[CNT_FINITE] : mp->last_n;
     mp->last.n_kept = r.counters[CNT_KEPT];
     mp->last.n_cells = r.counters[CNT_CELLS];
     mp->last.n_voxels = r.counters[CNT_VOXELS];
@@ -1356,6 +1390,45 @@ fdem_status fdem_mapper_integrate_with_cov(fdem_mapper* mp, const float* xyzw, c
   FDEM_REQUIRE(cov9 || n == 0, "cov9 is null");
   FDEM_TRY(integrate_common(mp, xyzw, cov9, intensity, rgb, n, Tbs, Twb));
   DeviceGuard dg(mp->map->device);
+  return finish_scan(mp, stats);
+}
+
+fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
+                                              const fdem_pointcloud2_layout* lo, const double* Tbs,
+                                              const double* Twb, fdem_scan_stats* stats) {
+  FDEM_REQUIRE(mp && lo && Tbs && Twb, "null argument");
+  DeviceGuard dg(mp->map->device);
+  // from_impl: empty message or no xyz fields -> empty cloud -> integrate() returns false
+  if (n == 0 || lo->off_x < 0 || lo->off_y < 0 || lo->off_z < 0) {
+    mp->last = fdem_scan_stats{};
+    mp->last_had_work = false;
+    if (stats) *stats = mp->last;
+    return FDEM_OK;
+  }
+  FDEM_REQUIRE(data, "data is null");
+  FDEM_REQUIRE(lo->point_step >= 12 && (lo->point_step & 3) == 0, "point_step must be a multiple of 4");
+  auto fits = [&](int32_t off, int32_t size) { return off >= 0 && off + size <= static_cast<int32_t>(lo->point_step); };
+  FDEM_REQUIRE(fits(lo->off_x, 4) && fits(lo->off_y, 4) && fits(lo->off_z, 4) &&
+                   !((lo->off_x | lo->off_y | lo->off_z) & 3), "x/y/z offsets out of range or unaligned");
+  if (lo->off_intensity >= 0) {
+    const int32_t t = lo->intensity_type;
+    const int32_t sz = t == 2 ? 1 : t == 4 ? 2 : t == 7 ? 4 : t == 8 ? 8 : 0;
+    // unknown datatypes read as 0.0f in the reference (readIntensity default branch)
+    if (sz) FDEM_REQUIRE(fits(lo->off_intensity, sz) && (lo->off_intensity % (sz >= 4 ? 4 : sz)) == 0,
+                         "intensity offset out of range or unaligned");
+  }
+  if (lo->off_rgb >= 0)
+    FDEM_REQUIRE(fits(lo->off_rgb, 4) && (lo->off_rgb & 3) == 0, "rgb offset out of range or unaligned");
+  ScanInputs in{};
+  in.raw = data;
+  in.layout = lo;
+  in.n = n;
+  in.input_frame = INPUT_SENSOR_FRAME;
+  in.Tbs = Tbs;
+  in.Twb = Twb;
+  in.robot_x = Twb[12];
+  in.robot_y = Twb[13];
+  FDEM_TRY(enqueue_scan(mp, in));
   return finish_scan(mp, stats);
 }
 

@@ -15,7 +15,7 @@ enum Counter : int {
   CNT_INSIDE = 1,    // kept points that fall inside the map (= valid sort keys)
   CNT_CELLS = 2,     // touched cells (segments)
   CNT_VOXELS = 3,    // voxelGrid(ANY) representatives
-  CNT_RAYS = 4,      // rays traced
+  CNT_FINITE = 4,    // PointCloud2 ingest: points with finite x, y, z (= cloud.size() after from())
   CNT_RC_SKIP = 5,   // 1 when raycasting preconditions failed (sensor outside map)
   CNT_REC_SLOTS = 8,   // tile path: record slots handed out to bucket segments
   CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
@@ -84,6 +84,16 @@ struct PreprocessParams {
   uint32_t invalid_key;  // = number of cells in this handle's slab
   uint32_t* bucket_count;  // tile path: per-bucket point histogram (null on the global-sort path)
   int32_t write_vals;      // global-sort path needs vals[i] = i
+  // sensor_msgs/PointCloud2 ingest (nanopcl::from(msg), nanopcl/bridge/ros/impl.hpp:180-270):
+  // when `raw` is set, point i is read from raw + i*point_step at the field offsets, points
+  // with a non-finite coordinate are dropped, intensity / packed rgb are unpacked into the
+  // SoA scratch the later kernels read
+  const uint8_t* raw;
+  uint32_t point_step;
+  int32_t off_x, off_y, off_z, off_intensity, off_rgb;
+  int32_t intensity_type;  // PointField datatype: 2 UINT8, 4 UINT16, 7 FLOAT32, 8 FLOAT64
+  float* out_intensity;
+  uint8_t* out_rgb;
 };
 
 // pointers to every layer the estimator kernel reads or writes (null when absent)
@@ -221,6 +231,8 @@ void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const fl
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,
                             const uint32_t* counters, size_t n_cells, cudaStream_t s,
                             LaunchCounter& lc);
+int launch_median_filter(const float* src, float* dst, const DeviceState* st, int kernel_size,
+                         int min_valid, cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 

@@ -142,7 +142,46 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   const int lane = threadIdx.x & 31;
   // the point load does not depend on the geometry: put it in flight first
   float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (i < p.n) q = __ldg(&p.xyzw[i]);
+  bool finite = true;
+  if (i < p.n) {
+    if (p.raw) {
+      // nanopcl::from(msg): x/y/z floats at their field offsets, w = 1; non-finite points are
+      // skipped before anything else sees them (bridge/ros/impl.hpp:237-244)
+      const uint8_t* pt = p.raw + static_cast<size_t>(i) * p.point_step;
+      q.x = __ldg(reinterpret_cast<const float*>(pt + p.off_x));
+      q.y = __ldg(reinterpret_cast<const float*>(pt + p.off_y));
+      q.z = __ldg(reinterpret_cast<const float*>(pt + p.off_z));
+      q.w = 1.0f;
+      finite = isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+      if (p.out_intensity) {
+        // readIntensity (bridge/ros/impl.hpp:106-121)
+        const uint8_t* f = pt + p.off_intensity;
+        float v = 0.0f;
+        switch (p.intensity_type) {
+          case 2: v = static_cast<float>(__ldg(f)); break;
+          case 4: v = static_cast<float>(__ldg(reinterpret_cast<const uint16_t*>(f))); break;
+          case 7: v = __ldg(reinterpret_cast<const float*>(f)); break;
+          case 8: {
+            const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(f));
+            const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(f) + 1);
+            v = static_cast<float>(__hiloint2double(static_cast<int>(hi), static_cast<int>(lo)));
+            break;
+          }
+          default: break;
+        }
+        p.out_intensity[i] = v;
+      }
+      if (p.out_rgb) {
+        // readRgb (bridge/ros/impl.hpp:170-177): packed 0x00RRGGBB in a 4-byte field
+        const uint32_t rgb = __ldg(reinterpret_cast<const uint32_t*>(pt + p.off_rgb));
+        p.out_rgb[static_cast<size_t>(i) * 3 + 0] = static_cast<uint8_t>((rgb >> 16) & 0xFF);
+        p.out_rgb[static_cast<size_t>(i) * 3 + 1] = static_cast<uint8_t>((rgb >> 8) & 0xFF);
+        p.out_rgb[static_cast<size_t>(i) * 3 + 2] = static_cast<uint8_t>(rgb & 0xFF);
+      }
+    } else {
+      q = __ldg(&p.xyzw[i]);
+    }
+  }
   if (threadIdx.x == 0) {
     GridGeom g = st_in->geom;
     if (p.local_mode) {
@@ -170,7 +209,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
       }
       q = transform_point(p.T1, q);                       // sensor -> base
       const float d2 = sqnorm3(q.x, q.y, q.z);            // cropRange, base frame
-      kept = (d2 >= p.range_min_sq && d2 <= p.range_max_sq) &&
+      kept = finite && (d2 >= p.range_min_sq && d2 <= p.range_max_sq) &&
              (q.z >= p.z_min && q.z <= p.z_max);          // cropZ, base frame
       if (kept) {
         q = transform_point(p.T2, q);                     // base -> map
@@ -199,6 +238,10 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
     if (p.write_vals) vals[i] = i;
   }
 
+  if (p.raw) {
+    const uint32_t fin_m = __ballot_sync(0xffffffffu, finite && i < p.n);
+    if (lane == 0 && fin_m) atomicAdd(&counters[CNT_FINITE], __popc(fin_m));
+  }
   const uint32_t kept_m = __ballot_sync(0xffffffffu, kept);
   const uint32_t inside_m = __ballot_sync(0xffffffffu, inside);
 

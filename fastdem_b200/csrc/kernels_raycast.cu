@@ -285,6 +285,52 @@ inpaint_iter_kernel(const float* __restrict__ src, float* __restrict__ dst,
   }
 }
 
+// applySpatialSmoothing (include/fastdem/postprocess/spatial_smoothing.hpp:38-67): median
+// (rank size/2) of the finite values in the K x K logical neighbourhood, centre included.
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+median_filter_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                     const DeviceState* __restrict__ st, int min_valid, int rows_local, int cols) {
+  const GridGeom g = st->geom;
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  constexpr int H = K / 2;
+  for (; i < n; i += stride) {
+    const float v = src[i];
+    float out = v;
+    if (isfinite(v)) {
+      const int bc = static_cast<int>(i / rows_local);
+      const int br = static_cast<int>(i - static_cast<size_t>(bc) * rows_local);
+      const int lr = wrap_index(br - g.start[0] + g.rows, g.rows);
+      const int lc = wrap_index(bc - g.start[1] + g.cols, g.cols);
+      float w[K * K];
+      int cnt = 0;
+#pragma unroll
+      for (int dr = -H; dr <= H; ++dr) {
+#pragma unroll
+        for (int dc = -H; dc <= H; ++dc) {
+          const int nr = lr + dr, nc = lc + dc;
+          if (nr < 0 || nr >= g.rows || nc < 0 || nc >= g.cols) continue;
+          const float val = src[static_cast<size_t>(wrap_index(nc + g.start[1], g.cols)) * rows_local +
+                                wrap_index(nr + g.start[0], g.rows)];
+          if (isfinite(val)) {
+            // insertion into the sorted prefix (tiny windows: 9 / 25 / 49 values)
+            int j = cnt++;
+            while (j > 0 && w[j - 1] > val) {
+              w[j] = w[j - 1];
+              --j;
+            }
+            w[j] = val;
+          }
+        }
+      }
+      if (cnt >= min_valid) out = w[cnt / 2];
+    }
+    dst[i] = out;
+  }
+}
+
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 8) {
   size_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
@@ -320,6 +366,19 @@ void launch_raycast_resolve(const RaycastParams& p, const DeviceState* /*st*/,
                             cudaStream_t s, LaunchCounter& lc) {
   raycast_resolve_kernel<<<grid_for(n_cells, kBlock), kBlock, 0, s>>>(p, lt, counters, n_cells);
   ++lc.mine;
+}
+int launch_median_filter(const float* src, float* dst, const DeviceState* st, int kernel_size,
+                         int min_valid, cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {
+  const int grid = grid_for(static_cast<size_t>(rows_local) * cols, kBlock);
+  switch (kernel_size) {
+    case 1: median_filter_kernel<1><<<grid, kBlock, 0, s>>>(src, dst, st, min_valid, rows_local, cols); break;
+    case 3: median_filter_kernel<3><<<grid, kBlock, 0, s>>>(src, dst, st, min_valid, rows_local, cols); break;
+    case 5: median_filter_kernel<5><<<grid, kBlock, 0, s>>>(src, dst, st, min_valid, rows_local, cols); break;
+    case 7: median_filter_kernel<7><<<grid, kBlock, 0, s>>>(src, dst, st, min_valid, rows_local, cols); break;
+    default: return 1;
+  }
+  ++lc.mine;
+  return 0;
 }
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {

@@ -231,6 +231,30 @@ fdem_status fdem_mapper_integrate_with_cov(fdem_mapper* m, const float* xyzw, co
                                            const double T_base_sensor[16],
                                            const double T_world_base[16], fdem_scan_stats* stats);
 
+/* The caller-side data format: a sensor_msgs/PointCloud2 message body handed over as is
+ * (what ros2/src/fastdem_ros_node.cpp:178-198 receives and nanopcl::from(msg) unpacks on the
+ * CPU, fastdem/lib/nanoPCL/include/nanopcl/bridge/ros/impl.hpp:180-270).  The unpacking —
+ * x/y/z at their field offsets, points with a non-finite coordinate dropped, intensity
+ * converted from its PointField datatype, packed 0x00RRGGBB colour — happens inside the
+ * first kernel, so the message crosses PCIe once, as one contiguous copy.
+ * Offsets as FieldOffsets::parse finds them (-1 = field absent).  4-byte fields must be
+ * 4-byte aligned within the point (they are in every message ROS drivers emit). */
+typedef struct fdem_pointcloud2_layout {
+  uint32_t point_step;     /* msg.point_step                                                */
+  int32_t off_x, off_y, off_z;
+  int32_t off_intensity;   /* "intensity"                                                   */
+  int32_t intensity_type;  /* PointField datatype: 2 UINT8, 4 UINT16, 7 FLOAT32, 8 FLOAT64   */
+  int32_t off_rgb;         /* "rgb" / "rgba"                                                */
+} fdem_pointcloud2_layout;
+/* integrate(nanopcl::from(msg), T_base_sensor, T_world_base); data = msg.data (HOST or DEVICE),
+ * num_points = msg.width * msg.height.  stats->n_input = points with finite coordinates. */
+fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* m, const uint8_t* data,
+                                              size_t num_points,
+                                              const fdem_pointcloud2_layout* layout,
+                                              const double T_base_sensor[16],
+                                              const double T_world_base[16],
+                                              fdem_scan_stats* stats);
+
 /* FastDEM::onScanPreprocessed payload (fastdem.cpp:139-141): the preprocessed cloud of the
  * LAST integrate, compacted in input order.  Buffers are HOST memory sized for n_kept:
  * xyzw [n_kept*4], cov9 [n_kept*9] (optional), src_index [n_kept] (optional). */
@@ -256,6 +280,12 @@ fdem_status fdem_voxel_grid_any(fdem_map* map, const float* xyzw, size_t n, floa
  * (fastdem/src/inpainting.cpp:21-67) */
 fdem_status fdem_inpaint(fdem_map* map, int32_t max_iterations, int32_t min_valid_neighbors,
                          int32_t inplace);
+
+/* fastdem::applySpatialSmoothing(map, layer, kernel_size, min_valid_neighbors)
+ * (fastdem/include/fastdem/postprocess/spatial_smoothing.hpp:38-67): in-place median filter;
+ * a missing layer is a no-op like in the reference.  kernel_size in {1, 3, 5, 7}. */
+fdem_status fdem_spatial_smoothing(fdem_map* map, const char* layer_name, int32_t kernel_size,
+                                   int32_t min_valid_neighbors);
 
 /* ── instrumentation ──────────────────────────────────────────────────────── */
 /* pipeline stages of one scan, in stream order */

@@ -1122,6 +1122,41 @@ inline void applyInpainting(ElevationMap& map, int max_iterations, int min_valid
   }
 }
 
+// ───────────────────────────── spatial smoothing ("next" row) ────────────────
+// applySpatialSmoothing (include/fastdem/postprocess/spatial_smoothing.hpp:38-67): median of
+// the finite values in the kernel_size x kernel_size logical neighbourhood (centre included),
+// in place with a double buffer; cells that are not finite or have fewer than
+// min_valid_neighbors finite values keep their value.  nth_element at size/2 == the element of
+// rank size/2 in sorted order.  kernel_size must be odd (the even-size region of nanoGrid is
+// not pinned by anything in the reference).
+inline void applySpatialSmoothing(ElevationMap& map, const std::string& layer_name,
+                                  int kernel_size = 3, int min_valid_neighbors = 5) {
+  if (!map.exists(layer_name)) return;
+  const Matrix input = map.get(layer_name);
+  Matrix& output = map.get(layer_name);
+  const int R = map.rows(), C = map.cols(), h = kernel_size / 2;
+  const Index st = map.startIndex();
+  std::vector<float> window;
+  for (int lc = 0; lc < C; ++lc) {
+    for (int lr = 0; lr < R; ++lr) {
+      const size_t l = map.lin(wrapIndex(lr + st.r, R), wrapIndex(lc + st.c, C));
+      if (!std::isfinite(input[l])) continue;
+      window.clear();
+      for (int dr = -h; dr <= h; ++dr)
+        for (int dc = -h; dc <= h; ++dc) {
+          const int nr = lr + dr, nc = lc + dc;
+          if (nr < 0 || nr >= R || nc < 0 || nc >= C) continue;
+          const float val = input[map.lin(wrapIndex(nr + st.r, R), wrapIndex(nc + st.c, C))];
+          if (std::isfinite(val)) window.push_back(val);
+        }
+      if (static_cast<int>(window.size()) < min_valid_neighbors) continue;
+      const size_t mid = window.size() / 2;
+      std::nth_element(window.begin(), window.begin() + mid, window.end());
+      output[l] = window[mid];
+    }
+  }
+}
+
 // ───────────────────────────── FastDEM pipeline ──────────────────────────────
 // fastdem/src/fastdem.cpp:122-162
 

@@ -338,3 +338,56 @@ void orc_inpaint(void* mp, int max_iterations, int min_valid_neighbors, int inpl
 float orc_pack_color(uint8_t r, uint8_t g, uint8_t b) { return packColor(r, g, b); }
 
 }  // extern "C"
+
+// ── sensor_msgs/PointCloud2 -> PointCloud (nanopcl::from, bridge/ros/impl.hpp:180-270) ──
+extern "C" {
+struct orc_pc2_layout {
+  uint32_t point_step;
+  int32_t off_x, off_y, off_z, off_intensity, intensity_type, off_rgb;
+};
+// Restates from_impl for the channels the path reads: points with a non-finite coordinate are
+// skipped; intensity converted per PointField datatype (readIntensity :106-121); rgb unpacked
+// from the packed field (readRgb :170-177).  Returns the number of points kept.
+int64_t orc_from_pointcloud2(const uint8_t* data, size_t n, const orc_pc2_layout* lo,
+                             float* out_xyzw, float* out_intensity, uint8_t* out_rgb) {
+  if (n == 0 || lo->off_x < 0 || lo->off_y < 0 || lo->off_z < 0) return 0;
+  int64_t k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t* pt = data + i * lo->point_step;
+    float x, y, z;
+    std::memcpy(&x, pt + lo->off_x, 4);
+    std::memcpy(&y, pt + lo->off_y, 4);
+    std::memcpy(&z, pt + lo->off_z, 4);
+    if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) continue;
+    out_xyzw[4 * k + 0] = x;
+    out_xyzw[4 * k + 1] = y;
+    out_xyzw[4 * k + 2] = z;
+    out_xyzw[4 * k + 3] = 1.0f;
+    if (lo->off_intensity >= 0 && out_intensity) {
+      const uint8_t* p = pt + lo->off_intensity;
+      float v = 0.0f;
+      switch (lo->intensity_type) {
+        case 2: v = static_cast<float>(*p); break;
+        case 4: { uint16_t u; std::memcpy(&u, p, 2); v = static_cast<float>(u); break; }
+        case 7: std::memcpy(&v, p, 4); break;
+        case 8: { double d; std::memcpy(&d, p, 8); v = static_cast<float>(d); break; }
+        default: v = 0.0f;
+      }
+      out_intensity[k] = v;
+    }
+    if (lo->off_rgb >= 0 && out_rgb) {
+      uint32_t rgb;
+      std::memcpy(&rgb, pt + lo->off_rgb, 4);
+      out_rgb[3 * k + 0] = static_cast<uint8_t>((rgb >> 16) & 0xFF);
+      out_rgb[3 * k + 1] = static_cast<uint8_t>((rgb >> 8) & 0xFF);
+      out_rgb[3 * k + 2] = static_cast<uint8_t>(rgb & 0xFF);
+    }
+    ++k;
+  }
+  return k;
+}
+}  // extern "C"
+
+extern "C" void orc_spatial_smoothing(void* mp, const char* layer, int kernel_size, int min_valid) {
+  applySpatialSmoothing(*static_cast<ElevationMap*>(mp), layer, kernel_size, min_valid);
+}

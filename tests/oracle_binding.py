@@ -22,7 +22,8 @@ _f64p = C.POINTER(C.c_double)
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        srcs = [ORACLE_DIR / "fdem_oracle.hpp", ORACLE_DIR / "fdem_oracle_capi.cpp"]
+        srcs = [ORACLE_DIR / "fdem_oracle.hpp", ORACLE_DIR / "fdem_oracle_capi.cpp",
+                ORACLE_DIR / "fdem_oracle_io.cpp"]
         if not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR)], check=True, stdout=subprocess.DEVNULL)
         L = C.CDLL(str(LIB_PATH))
@@ -272,3 +273,40 @@ def voxel_any(points, voxel):
     if k < 0:
         raise ValueError("voxel_size must be in [0.001, 100]")
     return out[:k].copy()
+
+
+def from_pointcloud2(data, n, layout):
+    """nanopcl::from(msg) on the oracle: -> (xyzw [k,4], intensity [k] | None, rgb [k,3] | None)."""
+    L = lib()
+    L.orc_from_pointcloud2.restype = C.c_int64
+    L.orc_from_pointcloud2.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    d = np.ascontiguousarray(data, np.uint8)
+    xyzw = np.empty((max(n, 1), 4), np.float32)
+    inten = np.empty(max(n, 1), np.float32) if layout.off_intensity >= 0 else None
+    rgb = np.empty((max(n, 1), 3), np.uint8) if layout.off_rgb >= 0 else None
+    k = L.orc_from_pointcloud2(d.ctypes.data, n, C.byref(layout), xyzw.ctypes.data,
+                               None if inten is None else inten.ctypes.data,
+                               None if rgb is None else rgb.ctypes.data)
+    return xyzw[:k], None if inten is None else inten[:k], None if rgb is None else rgb[:k]
+
+
+def spatial_smoothing(omap, layer, kernel_size=3, min_valid=5):
+    L = lib()
+    L.orc_spatial_smoothing.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.orc_spatial_smoothing(omap.h, layer.encode(), kernel_size, min_valid)
+
+
+def save_npz(omap, filename, frame_id="", layers=None):
+    L = lib()
+    L.orc_save_npz.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    return bool(L.orc_save_npz(omap.h, str(filename).encode(), frame_id.encode(),
+                               None if layers is None else "\n".join(layers).encode()))
+
+
+def load_npz(omap, filename):
+    """-> (ok, frame_id); re-creates the oracle map's geometry and layers from the file."""
+    L = lib()
+    L.orc_load_npz.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(256)
+    ok = bool(L.orc_load_npz(omap.h, str(filename).encode(), buf, 256))
+    return ok, buf.value.decode()

@@ -577,3 +577,24 @@ def test_inpainting_matches_oracle(fdem):  # test_postprocess.cpp:41-69
     fdem.applyInpainting(g, 2, 3, True)
     o.inpaint(2, 3, True)
     compare_layer("elevation", g.get("elevation"), o.get("elevation"), rtol=1e-6)
+
+
+def test_spatial_smoothing_matches_oracle(fdem):  # test_postprocess.cpp:249-271
+    rng = np.random.RandomState(13)
+    g = fdem.ElevationMap(10.0, 10.0, 0.5)
+    o = ob.OracleMap(10.0, 10.0, 0.5)
+    e = rng.uniform(0, 1, size=(20, 20)).astype(np.float32)
+    e[rng.uniform(size=e.shape) < 0.3] = np.nan
+    e[8:13, 8:13] = 1.0
+    e[10, 10] = 100.0
+    for m in (g, o):
+        m.set("elevation", np.asfortranarray(e))
+        m.move((1.0, -0.5))
+    _, c = g.getIndex((1.0 + 0.25, -0.5 + 0.25))
+    for k, mv in ((3, 5), (5, 7), (7, 3), (1, 1)):
+        fdem.applySpatialSmoothing(g, "elevation", k, mv)
+        ob.spatial_smoothing(o, "elevation", k, mv)
+        compare_layer("elevation", g.get("elevation"), o.get("elevation"), rtol=0, atol=0)
+    fdem.applySpatialSmoothing(g, "nonexistent_layer")   # no-op like the reference
+    with pytest.raises(fdem.FdemError):
+        fdem.applySpatialSmoothing(g, "elevation", 4, 5)

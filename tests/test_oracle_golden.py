@@ -563,3 +563,14 @@ def test_inpaint_fills_hole_from_eight_neighbours():
     m.inpaint(3, 2, False)
     assert abs(m.get("elevation_inpainted")[10, 10] - 1.0) < 0.01
     assert math.isnan(m.get("elevation")[10, 10])  # not in place
+
+
+def test_spatial_smoothing_removes_spike():  # test_postprocess.cpp:249-266
+    m = ob.OracleMap(10.0, 10.0, 0.5)
+    e = np.full((20, 20), NAN, np.float32)
+    e[8:13, 8:13] = 1.0
+    e[10, 10] = 100.0
+    m.set("elevation", e)
+    ob.spatial_smoothing(m, "elevation", 3, 5)
+    assert abs(m.get("elevation")[10, 10] - 1.0) < 0.01
+    ob.spatial_smoothing(m, "nonexistent_layer")  # :268-271 must not crash
