@@ -609,6 +609,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   pp.invalid_key = static_cast<uint32_t>(m->cells);
   const bool tile = mp->use_tile;
   pp.bucket_count = tile ? mp->tb.bucket_count : nullptr;
+  pp.bucket_bits = mp->tb.bucket_bits;
   pp.write_vals = tile ? 0 : 1;
   if (tile && mp->tile_dirty) {
     // first scan / after a failed scan: the L1 scratch K3t normally re-arms must be zero
@@ -783,7 +784,7 @@ void scan_node_args(ScanLaunch& L, uint32_t n, NodeArgs out[GN_COUNT]) {
   out[GN_K2].args[3] = &L.counters; out[GN_K2].args[4] = &L.lt;
   out[GN_SCATTER].d = desc_scatter_records(n);
   out[GN_SCATTER].args[0] = &L.sp;
-  out[GN_K3T].d = desc_tile_estimate(L.tb.n_buckets);
+  out[GN_K3T].d = desc_tile_estimate(L.tb.n_buckets, L.tb.bucket_bits);
   out[GN_K3T].args[0] = &L.ep; out[GN_K3T].args[1] = &L.tb; out[GN_K3T].args[2] = &L.counters;
   out[GN_K3T].args[3] = &L.st_next; out[GN_K3T].args[4] = &L.pub;
 }
@@ -1295,7 +1296,11 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
     mp->use_graph = !(genv && std::string(genv) == "0");
     const char* penv = std::getenv("FDEM_PDL");
     mp->use_pdl = penv && std::string(penv) == "1";  // measured: no gain inside a graph; opt-in
-    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + kBucketCells - 1) >> kBucketBits);
+    // bucket size: 1024 cells (256-thread CTAs, 3 per SM) unless FDEM_BUCKET_BITS=9
+    // (512 cells, 128-thread CTAs, 6 per SM)
+    const char* benv = std::getenv("FDEM_BUCKET_BITS");
+    mp->tb.bucket_bits = (benv && std::string(benv) == "9") ? 9u : 10u;
+    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + (1ull << mp->tb.bucket_bits) - 1) >> mp->tb.bucket_bits);
     const size_t nb = std::max<size_t>(mp->tb.n_buckets, 1) * sizeof(uint32_t);
     cudaError_t e2 = cudaMalloc(&mp->tb.bucket_count, nb);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_offset, nb);

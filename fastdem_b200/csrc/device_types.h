@@ -27,8 +27,7 @@ enum Counter : int {
 // L1 = radix partition of the scan into buckets of 2^kBucketBits consecutive cell keys
 // (global, one pass: histogram in K1, segment allocation in K2, scatter kernel);
 // L2 = per-bucket sort + warp-segmented reduce in shared memory (K3t).
-constexpr int kBucketBits = 10;
-constexpr uint32_t kBucketCells = 1u << kBucketBits;
+// The bucket size is a per-mapper choice (bucket_bits = 9 or 10): K3t is compiled for both.
 
 // one run of same-cell points, pre-reduced by the scatter kernel (fields = CellObs)
 struct alignas(32) CellRecord {
@@ -47,6 +46,7 @@ struct TileBuffers {
   uint4* bucket_list;       // [n_buckets] non-empty buckets: {bucket, first slot, points, 0} (K2)
   CellRecord* records;      // [capacity in points]
   uint32_t n_buckets;
+  uint32_t bucket_bits;     // cells per bucket = 1 << bucket_bits
 };
 
 // State that survives from scan to scan and is decided on the device (so a stream of
@@ -83,6 +83,7 @@ struct PreprocessParams {
   int32_t local_mode;
   uint32_t invalid_key;  // = number of cells in this handle's slab
   uint32_t* bucket_count;  // tile path: per-bucket point histogram (null on the global-sort path)
+  uint32_t bucket_bits;
   int32_t write_vals;      // global-sort path needs vals[i] = i
   // sensor_msgs/PointCloud2 ingest (nanopcl::from(msg), nanopcl/bridge/ros/impl.hpp:180-270):
   // when `raw` is set, point i is read from raw + i*point_step at the field offsets, points
@@ -207,7 +208,7 @@ KernelDesc desc_preprocess_bin(uint32_t n);
 KernelDesc desc_commit();
 KernelDesc desc_publish();
 KernelDesc desc_scatter_records(uint32_t n);
-KernelDesc desc_tile_estimate(uint32_t n_buckets);
+KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits);
 // tile path (kernels_tile.cu)
 void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc);
 void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,

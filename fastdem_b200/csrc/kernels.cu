@@ -248,7 +248,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   // tile path, L1 histogram: points per bucket of 2^kBucketBits consecutive cell keys.
   // One atomic per (warp, bucket) — scan-sized scratch, never map state.
   if (p.bucket_count && inside) {
-    const uint32_t bucket = key >> kBucketBits;
+    const uint32_t bucket = key >> p.bucket_bits;
     const uint32_t peers = __match_any_sync(inside_m, bucket);
     if (lane == __ffs(peers) - 1) atomicAdd(&p.bucket_count[bucket], __popc(peers));
   }

@@ -10,14 +10,16 @@
 //         scatter_records_kernel: consecutive same-cell points of a warp are pre-reduced
 //              with a segmented shuffle scan (LiDAR rings / image rows are coherent), and
 //              one 32-byte CellRecord per run is written into its bucket's segment
-//   L2  tile_estimate_kernel, one CTA per non-empty bucket (dynamic work list):
+//   L2  tile_estimate_kernel, one CTA per non-empty bucket (static round-robin work list):
 //         the bucket's records are staged into shared memory with TMA bulk copies
 //         (cp.async.bulk + mbarrier), counting-sorted by cell inside shared memory, and
-//         folded per cell into shared-memory accumulators — the owner thread walks a
-//         cell's (few) sorted records; crowded cells get a warp and a shuffle butterfly.
-//         Then the bucket's touched cells are compacted and each gets ONE Kalman / P2
-//         step: every layer value is loaded once (batched) and stored once with a plain
-//         store, neighbouring threads on neighbouring cells.
+//         reduced per cell — the owner thread walks a cell's (few) sorted records; crowded
+//         cells get a warp and a shuffle butterfly.  A bucket whose records fit one chunk
+//         (the common case) is reduced straight into a compact list of touched cells; a
+//         bucket that needs several chunks goes through per-cell accumulators.  Each
+//         touched cell then gets ONE Kalman / P2 step: every layer value is loaded once
+//         (batched) and stored once with a plain store, neighbouring threads on
+//         neighbouring cells.
 //
 // Atomics appear only on scan-sized scratch (bucket cursors, shared-memory bins, scan
 // statistics) — never on estimator state.  Results are independent of every ordering the
@@ -32,9 +34,7 @@ namespace fdem {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 1024;  // records staged per bulk copy (32 KiB)
+constexpr int kThreads = 256;  // scatter kernel
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kHotCell = 48;  // records of one cell in one chunk above which a warp takes over
 
@@ -126,7 +126,7 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   const bool emit = tail && key != INV;
   const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
   if (emit) {
-    const uint32_t bucket = key >> kBucketBits;
+    const uint32_t bucket = key >> p.tb.bucket_bits;
     // one cursor atomic per (warp, bucket); scratch, not map state
     const uint32_t peers = __match_any_sync(emit_m, bucket);
     const int leader = __ffs(peers) - 1;
@@ -135,7 +135,8 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = p.tb.bucket_offset[bucket] + base + __popc(peers & ((1u << lane) - 1u));
     uint4* dst = reinterpret_cast<uint4*>(p.tb.records + slot);
-    dst[0] = make_uint4(key & (kBucketCells - 1u), __float_as_uint(v.mz), __float_as_uint(v.mv), v.mi);
+    dst[0] = make_uint4(key & ((1u << p.tb.bucket_bits) - 1u), __float_as_uint(v.mz),
+                        __float_as_uint(v.mv), v.mi);
     dst[1] = make_uint4(__float_as_uint(v.xz), __float_as_uint(v.it), v.fi, v.li);
   }
 }
@@ -153,33 +154,68 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define K3T_MARK(i) do { if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[i] = clock64() - t_entry; } while (0)
 
 // ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
+// Compiled for 512-cell buckets (128 threads, ~34 KiB smem, 6 CTAs/SM) and 1024-cell
+// buckets (256 threads, ~68 KiB, 3 CTAs/SM); the mapper picks one (fdem_mapper_create).
+template <int BITS>
+struct TileCfg {
+  static constexpr int kCells = 1 << BITS;
+  static constexpr int kThr = kCells / 4;      // 4 cells per thread
+  static constexpr int kWarps = kThr / 32;
+  static constexpr int kChunk = kCells;        // records staged per bulk copy (32 B each)
+  static constexpr int kMinBlocks = BITS == 9 ? 6 : 3;
+};
+
+template <int BITS>
 struct TileSmem {
-  CellRecord stage[kChunk];          // TMA destination
-  uint32_t binoff[kBucketCells];     // counting-sort bins (count -> offset -> cursor)
-  float a_mz[kBucketCells];          // per-cell accumulators for the whole bucket
-  float a_mv[kBucketCells];
-  uint32_t a_mi[kBucketCells];
-  float a_xz[kBucketCells];
-  float a_it[kBucketCells];
-  uint32_t a_fi[kBucketCells];
-  uint32_t a_li[kBucketCells];
-  uint16_t perm[kChunk];             // sorted position -> index into stage
-  uint16_t tlist[kBucketCells];      // compacted list of the bucket's touched cells
+  using C = TileCfg<BITS>;
+  CellRecord stage[C::kChunk];       // TMA destination
+  uint32_t binoff[C::kCells];        // counting-sort bins (count -> offset -> cursor)
+  // reduced observations: slot = position in the touched list (single-chunk bucket) or
+  // the cell itself (multi-chunk bucket, used as accumulators)
+  float a_mz[C::kCells];
+  float a_mv[C::kCells];
+  uint32_t a_mi[C::kCells];
+  float a_xz[C::kCells];
+  float a_it[C::kCells];
+  uint32_t a_fi[C::kCells];
+  uint32_t a_li[C::kCells];
+  uint16_t perm[C::kChunk];          // sorted position -> index into stage
+  uint16_t tlist[C::kCells];         // compacted list of the bucket's touched cells
   uint64_t mbar;
-  uint32_t warp_sums[kWarps];
+  uint32_t warp_sums[C::kWarps];
   uint32_t n_touched;
   uint32_t list_base;
   uint32_t is_last;
   uint32_t n_hot;
-  uint16_t hot_cell[kChunk / kHotCell + 1];  // cells deferred to the warp-cooperative path
+  uint16_t hot_cell[C::kChunk / kHotCell + 1];  // cells deferred to the warp-cooperative path
+  uint16_t hot_slot[C::kChunk / kHotCell + 1];  // where their result goes
 };
 
-__global__ void __launch_bounds__(kThreads, 3)
+template <typename S_>
+__device__ __forceinline__ CellObs acc_load(const S_& S, uint32_t a) {
+  CellObs t;
+  t.mz = S.a_mz[a]; t.mv = S.a_mv[a]; t.mi = S.a_mi[a]; t.xz = S.a_xz[a];
+  t.it = S.a_it[a]; t.fi = S.a_fi[a]; t.li = S.a_li[a];
+  return t;
+}
+template <typename S_>
+__device__ __forceinline__ void acc_store(S_& S, uint32_t a, const CellObs& t) {
+  S.a_mz[a] = t.mz; S.a_mv[a] = t.mv; S.a_mi[a] = t.mi; S.a_xz[a] = t.xz;
+  S.a_it[a] = t.it; S.a_fi[a] = t.fi; S.a_li[a] = t.li;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(TileCfg<BITS>::kThr, TileCfg<BITS>::kMinBlocks)
 tile_estimate_kernel(const __grid_constant__ EstimateParams p,
                      const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters,
                      DeviceState* __restrict__ st_out, const __grid_constant__ PublishArgs pub) {
+  using C = TileCfg<BITS>;
+  constexpr int kThr = C::kThr;
+  constexpr int kCells = C::kCells;
+  constexpr int kChunk = C::kChunk;
+  constexpr int kWarps = C::kWarps;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+  TileSmem<BITS>& S = *reinterpret_cast<TileSmem<BITS>*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -190,20 +226,21 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   // prologue that needs nothing from the scatter kernel: overlaps its tail under PDL
   if (tid == 0) mbar_init(&S.mbar, 1);
   uint32_t phase = 0;
-  for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
-    S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
-    S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
-    S.binoff[c] = 0;
-  }
+  for (int c = tid; c < kCells; c += kThr) S.binoff[c] = 0;
   if (tid == 0) { S.n_touched = 0; S.n_hot = 0; }
   pdl_wait();  // the bucket segments are complete and visible from here on
   K3T_MARK(0);   // prologue done
+  // the job count and this CTA's first list entry are independent loads: one round trip
+  // (the list has one slot per bucket and the grid never exceeds that, so the speculative
+  // read is in bounds; it is used only when job < n_jobs, i.e. when this scan wrote it)
   const uint32_t n_jobs = counters[CNT_BUCKETS];
+  uint4 entry_next = tb.bucket_list[blockIdx.x];
 
   // static round-robin over the non-empty buckets K2 listed: no work-fetch atomics
   for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
     __syncthreads();  // previous bucket completely done (also publishes the mbarrier init)
-    const uint4 entry = tb.bucket_list[job];  // {bucket, first record slot, points, -}
+    const uint4 entry = entry_next;  // {bucket, first record slot, points, -}
+    if (job + gridDim.x < n_jobs) entry_next = tb.bucket_list[job + gridDim.x];  // prefetch
     const uint32_t b = entry.x;
     const uint32_t off = entry.y;
     // Stage the first chunk right away.  The record count is not known yet (it is being
@@ -219,6 +256,12 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
     const uint32_t nrec = tb.bucket_cursor[b];  // in flight together with the bulk copy
     K3T_MARK(1);  // job entry + record count loaded
     if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[15] = nrec;
+    // single-chunk bucket: cells are reduced from scratch straight into the touched list;
+    // multi-chunk bucket: per-cell accumulators carry a cell across chunks
+    const bool single = nrec <= static_cast<uint32_t>(kChunk);
+    if (!single) {
+      for (int c = tid; c < kCells; c += kThr) acc_store(S, c, obs_identity());
+    }
 
     for (uint32_t cs = 0; cs < nrec; cs += kChunk) {
       const uint32_t cn = min(static_cast<uint32_t>(kChunk), nrec - cs);
@@ -230,7 +273,7 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
           tma_load_1d(S.stage, tb.records + off + cs,
                       cn * static_cast<uint32_t>(sizeof(CellRecord)), &S.mbar);
         }
-        for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) S.binoff[c] = 0;
+        for (int c = tid; c < kCells; c += kThr) S.binoff[c] = 0;
       }
       __syncthreads();
       mbar_wait(&S.mbar, phase);
@@ -238,10 +281,10 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       if (cs == 0) K3T_MARK(2);  // first chunk staged
 
       // ── counting sort by cell, in shared memory ──
-      for (uint32_t e = tid; e < cn; e += kThreads) atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
+      for (uint32_t e = tid; e < cn; e += kThr) atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
       __syncthreads();
       {
-        // exclusive scan of the 1024 bins: 4 consecutive bins per thread
+        // exclusive scan of the bins: 4 consecutive bins per thread
         const uint32_t v0 = S.binoff[tid * 4 + 0], v1 = S.binoff[tid * 4 + 1];
         const uint32_t v2 = S.binoff[tid * 4 + 2], v3 = S.binoff[tid * 4 + 3];
         const uint32_t t = v0 + v1 + v2 + v3;
@@ -264,7 +307,7 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
         S.binoff[tid * 4 + 3] = base + v0 + v1 + v2;
       }
       __syncthreads();
-      for (uint32_t e = tid; e < cn; e += kThreads) {
+      for (uint32_t e = tid; e < cn; e += kThr) {
         const uint32_t pos = atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
         S.perm[pos] = static_cast<uint16_t>(e);
       }
@@ -273,38 +316,44 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
 
       // ── per-cell reduction of the sorted chunk ──
       // After the counting sort the records of cell c occupy sorted positions
-      // [binoff[c-1], binoff[c]).  Thread t owns cells t, t+256, t+512, t+768 of the
-      // bucket: it folds each cell's few records (pre-reduced runs, typically 0-3) into
-      // that cell's accumulator, which nobody else touches.  Cells with many records in
-      // this chunk are deferred to the warp-cooperative path below.
-      uint32_t my_hot = 0;  // bit r set: my r-th cell was deferred
+      // [binoff[c-1], binoff[c]).  Thread t owns cells t, t+kThr, t+2kThr, t+3kThr of the
+      // bucket and folds each cell's few records (pre-reduced runs, typically 0-3).  Cells
+      // with many records in this chunk are deferred to the warp-cooperative path below.
 #pragma unroll
-      for (int r = 0; r < static_cast<int>(kBucketCells) / kThreads; ++r) {
-        const int c = tid + r * kThreads;
+      for (int r = 0; r < kCells / kThr; ++r) {
+        const int c = tid + r * kThr;
         const uint32_t s0 = c ? S.binoff[c - 1] : 0u;
         const uint32_t e0 = S.binoff[c];
         const uint32_t cnt = e0 - s0;
+        uint32_t slot = static_cast<uint32_t>(c);
+        if (single) {
+          // the cell's slot in the touched list (the loop is warp-uniform up to here)
+          const uint32_t tm = __ballot_sync(0xffffffffu, cnt != 0);
+          uint32_t wbase = 0;
+          if (lane == 0 && tm) wbase = atomicAdd(&S.n_touched, __popc(tm));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          slot = wbase + __popc(tm & ((1u << lane) - 1u));
+          if (cnt) S.tlist[slot] = static_cast<uint16_t>(c);
+        }
         if (cnt == 0) continue;
         if (cnt > kHotCell) {
           const uint32_t h = atomicAdd(&S.n_hot, 1u);
           S.hot_cell[h] = static_cast<uint16_t>(c);
-          my_hot |= 1u << r;
+          S.hot_slot[h] = static_cast<uint16_t>(slot);
           continue;
         }
-        CellObs a;
-        a.mz = S.a_mz[c]; a.mv = S.a_mv[c]; a.mi = S.a_mi[c]; a.xz = S.a_xz[c];
-        a.it = S.a_it[c]; a.fi = S.a_fi[c]; a.li = S.a_li[c];
+        CellObs a = single ? obs_identity() : acc_load(S, slot);
         for (uint32_t j = s0; j < e0; ++j) a = obs_combine(a, obs_of(S.stage[S.perm[j]]));
-        S.a_mz[c] = a.mz; S.a_mv[c] = a.mv; S.a_mi[c] = a.mi; S.a_xz[c] = a.xz;
-        S.a_it[c] = a.it; S.a_fi[c] = a.fi; S.a_li[c] = a.li;
+        acc_store(S, slot, a);
       }
       __syncthreads();
       const uint32_t n_hot = S.n_hot;
       if (n_hot) {
         // crowded cells: one warp per cell, lanes stride over its records, butterfly
-        // reduction over warp shuffles, lane 0 merges into the accumulator
+        // reduction over warp shuffles, lane 0 merges into the cell's slot
         for (uint32_t h = warp; h < n_hot; h += kWarps) {
           const int c = S.hot_cell[h];
+          const uint32_t slot = S.hot_slot[h];
           const uint32_t s0 = c ? S.binoff[c - 1] : 0u;
           const uint32_t e0 = S.binoff[c];
           CellObs a = obs_identity();
@@ -322,40 +371,38 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
             a = obs_combine(a, o);
           }
           if (lane == 0) {
-            CellObs t;
-            t.mz = S.a_mz[c]; t.mv = S.a_mv[c]; t.mi = S.a_mi[c]; t.xz = S.a_xz[c];
-            t.it = S.a_it[c]; t.fi = S.a_fi[c]; t.li = S.a_li[c];
-            t = obs_combine(t, a);
-            S.a_mz[c] = t.mz; S.a_mv[c] = t.mv; S.a_mi[c] = t.mi; S.a_xz[c] = t.xz;
-            S.a_it[c] = t.it; S.a_fi[c] = t.fi; S.a_li[c] = t.li;
+            if (!single) a = obs_combine(acc_load(S, slot), a);
+            acc_store(S, slot, a);
           }
         }
         __syncthreads();
         if (tid == 0) S.n_hot = 0;
       }
-      (void)my_hot;
-      __syncthreads();  // accumulators + stage reads done before the next chunk / final pass
+      __syncthreads();  // results + stage reads done before the next chunk / final pass
       if (cs == 0) K3T_MARK(4);  // first chunk reduced
     }
     K3T_MARK(5);  // all chunks done
 
-    // ── compact the bucket's touched cells (ascending by construction of the ranks) ──
+    if (!single) {
+      // ── compact the bucket's touched cells out of the accumulators ──
 #pragma unroll
-    for (int r = 0; r < static_cast<int>(kBucketCells) / kThreads; ++r) {
-      const int c = tid + r * kThreads;
-      const bool touched = S.a_fi[c] != kNone;
-      const uint32_t tm = __ballot_sync(0xffffffffu, touched);
-      uint32_t wbase = 0;
-      if (lane == 0 && tm) wbase = atomicAdd(&S.n_touched, __popc(tm));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (touched) S.tlist[wbase + __popc(tm & ((1u << lane) - 1u))] = static_cast<uint16_t>(c);
+      for (int r = 0; r < kCells / kThr; ++r) {
+        const int c = tid + r * kThr;
+        const bool touched = S.a_fi[c] != kNone;
+        const uint32_t tm = __ballot_sync(0xffffffffu, touched);
+        uint32_t wbase = 0;
+        if (lane == 0 && tm) wbase = atomicAdd(&S.n_touched, __popc(tm));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (touched) S.tlist[wbase + __popc(tm & ((1u << lane) - 1u))] = static_cast<uint16_t>(c);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     const uint32_t nt = S.n_touched;
     K3T_MARK(6);  // touched cells compacted
-    if (tid == 0) {
+    if (tid == kThr - 1) {
       // reserve this bucket's slice of the touched-cell list (next scan's obstacle reset)
-      // and count the cells; the round trip overlaps the estimator work below
+      // and count the cells.  Done by the thread least likely to own an estimator step, so
+      // the atomic's round trip does not sit in front of a cell's loads.
       S.list_base = nt ? atomicAdd(&st_out->touched_count, nt) : 0u;
       if (nt) atomicAdd(&counters[CNT_CELLS], nt);
       tb.bucket_count[b] = 0;   // re-arm the L1 scratch for the next scan
@@ -364,32 +411,26 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
 
     // ── estimator: one Kalman / P2 step per touched cell; each layer value is loaded once
     //    (batched) and stored once; neighbouring threads handle neighbouring cells ──
-    const uint32_t key_base = b << kBucketBits;
-    for (uint32_t t = tid; t < nt; t += kThreads) {
+    const uint32_t key_base = b << BITS;
+    for (uint32_t t = tid; t < nt; t += kThr) {
       const uint32_t c = S.tlist[t];
-      CellObs v;
-      v.mz = S.a_mz[c]; v.mv = S.a_mv[c]; v.mi = S.a_mi[c]; v.xz = S.a_xz[c];
-      v.it = S.a_it[c]; v.fi = S.a_fi[c]; v.li = S.a_li[c];
+      const CellObs v = acc_load(S, single ? t : c);
       apply_observation(p, key_base + c, v);
     }
     __syncthreads();
     K3T_MARK(7);  // estimator done
     const uint32_t lb = S.list_base;
-    for (uint32_t t = tid; t < nt; t += kThreads) {
+    for (uint32_t t = tid; t < nt; t += kThr) {
       const uint32_t c = S.tlist[t];
       p.touched_keys[lb + t] = key_base + c;
-      if (p.touched_minz) p.touched_minz[lb + t] = S.a_mz[c];
+      if (p.touched_minz) p.touched_minz[lb + t] = S.a_mz[single ? t : c];
     }
     K3T_MARK(8);  // touched list written
     first_job = false;
     if (job + gridDim.x < n_jobs) {
-      // another bucket follows on this CTA: re-arm the accumulators and bins
+      // another bucket follows on this CTA: re-arm the bins
       __syncthreads();
-      for (int c = tid; c < static_cast<int>(kBucketCells); c += kThreads) {
-        S.a_mz[c] = FLT_MAX; S.a_mv[c] = 0.0f; S.a_mi[c] = kNone; S.a_xz[c] = -FLT_MAX;
-        S.a_it[c] = -INFINITY; S.a_fi[c] = kNone; S.a_li[c] = 0u;
-        S.binoff[c] = 0;
-      }
+      for (int c = tid; c < kCells; c += kThr) S.binoff[c] = 0;
       if (tid == 0) S.n_touched = 0;
     }
   }
@@ -429,6 +470,12 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x + 1] = globaltimer_ns();
 }
 
+template <int BITS>
+uint32_t tile_grid(uint32_t n_buckets) {
+  const uint32_t cap = 148u * static_cast<uint32_t>(TileCfg<BITS>::kMinBlocks);
+  return n_buckets < cap ? n_buckets : cap;
+}
+
 }  // namespace
 
 int tile_estimate_debug_cta_ns(unsigned long long* out1024) {
@@ -440,9 +487,13 @@ int tile_estimate_debug_clocks(long long* out16) {
 }
 
 int tile_estimate_configure() {
-  return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel,
+  cudaError_t e = cudaFuncSetAttribute(tile_estimate_kernel<9>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(sizeof(TileSmem<9>)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel<10>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(sizeof(TileSmem))));
+                                               static_cast<int>(sizeof(TileSmem<10>))));
 }
 
 void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc) {
@@ -454,9 +505,14 @@ void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounte
 void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
                           DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
                           LaunchCounter& lc) {
-  // CTAs stride over the non-empty-bucket list; 3 CTAs/SM fit in shared memory
-  const uint32_t grid = min(tb.n_buckets, 148u * 3u);
-  tile_estimate_kernel<<<grid, kThreads, sizeof(TileSmem), s>>>(p, tb, counters, st_out, pub);
+  // CTAs stride over the non-empty-bucket list; one wave of co-resident CTAs at most
+  if (tb.bucket_bits == 9) {
+    tile_estimate_kernel<9><<<tile_grid<9>(tb.n_buckets), TileCfg<9>::kThr, sizeof(TileSmem<9>), s>>>(
+        p, tb, counters, st_out, pub);
+  } else {
+    tile_estimate_kernel<10><<<tile_grid<10>(tb.n_buckets), TileCfg<10>::kThr, sizeof(TileSmem<10>), s>>>(
+        p, tb, counters, st_out, pub);
+  }
   ++lc.mine;
 }
 
@@ -467,9 +523,11 @@ KernelDesc desc_scatter_records(uint32_t n) {
   return KernelDesc{reinterpret_cast<const void*>(&scatter_records_kernel),
                     dim3((n + kThreads - 1) / kThreads), dim3(kThreads), 0};
 }
-KernelDesc desc_tile_estimate(uint32_t n_buckets) {
-  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel),
-                    dim3(n_buckets < 148u * 3u ? n_buckets : 148u * 3u), dim3(kThreads),
-                    sizeof(TileSmem)};
+KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits) {
+  if (bucket_bits == 9)
+    return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel<9>),
+                      dim3(tile_grid<9>(n_buckets)), dim3(TileCfg<9>::kThr), sizeof(TileSmem<9>)};
+  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel<10>),
+                    dim3(tile_grid<10>(n_buckets)), dim3(TileCfg<10>::kThr), sizeof(TileSmem<10>)};
 }
 }  // namespace fdem
