@@ -48,7 +48,7 @@ class FdemConfig(C.Structure):
 
 class FdemScanStats(C.Structure):
     _fields_ = [("n_input", C.c_int64), ("n_kept", C.c_int64), ("n_cells", C.c_int64),
-                ("n_voxels", C.c_int64), ("integrated", C.c_int32), ("_pad", C.c_int32)]
+                ("n_voxels", C.c_int64), ("integrated", C.c_int32), ("voxel_box_violations", C.c_int32)]
 
 
 class FdemPointCloud2Layout(C.Structure):

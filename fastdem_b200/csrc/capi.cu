@@ -441,9 +441,16 @@ EstLayers est_layers(fdem_map* m) {
   return L;
 }
 
+// scratch for the ray ordering (keys / values, unsorted + sorted, CUB temp)
+struct RayScratch {
+  uint32_t *keys, *vals, *skeys, *svals;
+  void* temp;
+  size_t temp_bytes;
+};
 fdem_status raycast_device(fdem_map* m, const fdem_config& cfg, const float origin[3],
                            const float4* pts, const uint32_t* sel, const DeviceState* st,
-                           uint32_t n_max, uint32_t* counters);
+                           uint32_t n_max, uint32_t* counters, const RayScratch& rs);
+bool voxel_box(const fdem_config& cfg, const float* T2, float voxel, VoxelBox* box);
 fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s);
 
 cudaEvent_t take_event(fdem_mapper* mp) {
@@ -734,13 +741,28 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
       if (voxel < 0.001f || voxel > 100.0f) {
         launch_status = set_error(FDEM_ERR_INVALID_ARGUMENT, "voxel_size must be in [0.001, 100]");
       } else {
-        launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vals, s, m->lc);
-        cudaError_t se = sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys,
-                                        mp->d_svkeys, mp->d_vals, mp->d_svals, n, 64, s, m->lc);
+        // voxelGrid(ANY): sort by voxel key.  The crop filters usually bound the kept points
+        // to a box small enough for 32-bit keys (4 radix passes instead of 8).
+        VoxelBox box{};
+        cudaError_t se = cudaSuccess;
+        if (voxel_box(cfg, pp.T2, voxel, &box)) {
+          const int bits = box.bx + box.by + box.bz + 1;
+          launch_voxel_keys32(mp->d_pm, n, 1.0f / voxel, box, mp->d_keys, mp->d_vals, mp->d_counters, s, m->lc);
+          se = sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_keys, mp->d_skeys,
+                              mp->d_vals, mp->d_svals, n, bits, s, m->lc);
+          launch_voxel_select32(mp->d_skeys, mp->d_svals, n, box.invalid_key, mp->d_counters, mp->d_sel, s, m->lc);
+        } else {
+          launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vals, s, m->lc);
+          se = sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys, mp->d_svkeys,
+                              mp->d_vals, mp->d_svals, n, 64, s, m->lc);
+          launch_voxel_select(mp->d_svkeys, mp->d_svals, n, mp->d_counters, mp->d_sel, s, m->lc);
+        }
         if (se != cudaSuccess) launch_status = set_error(FDEM_ERR_CUDA, cudaGetErrorString(se));
-        launch_voxel_select(mp->d_svkeys, mp->d_svals, n, mp->d_counters, mp->d_sel, s, m->lc);
-        if (launch_status == FDEM_OK)
-          launch_status = raycast_device(m, cfg, origin, mp->d_pm, mp->d_sel, st_out, n, mp->d_counters);
+        if (launch_status == FDEM_OK) {
+          const RayScratch rs{mp->d_keys, mp->d_vals, mp->d_skeys, mp->d_svals, mp->d_sort_temp,
+                              mp->sort_temp_bytes};
+          launch_status = raycast_device(m, cfg, origin, mp->d_pm, mp->d_sel, st_out, n, mp->d_counters, rs);
+        }
       }
     }
     mark(FDEM_STAGE_COUNT);
@@ -868,7 +890,7 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
     mp->last.n_cells = r.counters[CNT_CELLS];
     mp->last.n_voxels = r.counters[CNT_VOXELS];
     mp->last.integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
-    mp->last._pad = 0;
+    mp->last.voxel_box_violations = static_cast<int32_t>(r.counters[CNT_VOX_VIOLATION]);
     if (mp->last.n_cells > 0) m->obstacle_full_clear = false;
   }
   mp->pending = false;
@@ -1472,7 +1494,7 @@ fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stat
   stats->n_cells = r.counters[CNT_CELLS];
   stats->n_voxels = r.counters[CNT_VOXELS];
   stats->integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
-  stats->_pad = 0;
+  stats->voxel_box_violations = static_cast<int32_t>(r.counters[CNT_VOX_VIOLATION]);
   if (ticket + 1 == m->seq) {  // newest scan: its committed geometry is the map's geometry
     m->geom = r.state.geom;
     m->geom_stale = false;

@@ -17,6 +17,7 @@ enum Counter : int {
   CNT_VOXELS = 3,    // voxelGrid(ANY) representatives
   CNT_FINITE = 4,    // PointCloud2 ingest: points with finite x, y, z (= cloud.size() after from())
   CNT_RC_SKIP = 5,   // 1 when raycasting preconditions failed (sensor outside map)
+  CNT_VOX_VIOLATION = 6,  // points outside the host-predicted voxel box (must stay 0)
   CNT_REC_SLOTS = 8,   // tile path: record slots handed out to bucket segments
   CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
   CNT_WORK = 10,       // tile path: K3t's dynamic work counter
@@ -226,9 +227,25 @@ void launch_voxel_keys(const float4* pm, uint32_t n, float inv_voxel, uint64_t* 
                        uint32_t* vals, cudaStream_t s, LaunchCounter& lc);
 void launch_voxel_select(const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
                          uint32_t* counters, uint32_t* out_sel, cudaStream_t s, LaunchCounter& lc);
+// compact 32-bit voxel keys: box of the kept points predicted by the host from the crop filters
+struct VoxelBox {
+  int32_t x0, y0, z0;   // voxel coordinate of the box corner (after the reference's clamp)
+  int32_t bx, by, bz;   // bits per axis; bx + by + bz <= 31
+  uint32_t invalid_key; // 1 << (bx + by + bz): sorts after every valid key
+};
+void launch_voxel_keys32(const float4* pm, uint32_t n, float inv_voxel, const VoxelBox& box,
+                         uint32_t* keys, uint32_t* vals, uint32_t* counters, cudaStream_t s,
+                         LaunchCounter& lc);
+void launch_voxel_select32(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                           uint32_t invalid_key, uint32_t* counters, uint32_t* out_sel,
+                           cudaStream_t s, LaunchCounter& lc);
+int ray_key_bits();
+void launch_ray_keys(const RaycastParams& p, const DeviceState* st, const float4* pts,
+                     const uint32_t* sel, uint32_t n_max, uint32_t* counters, uint32_t* rkeys,
+                     uint32_t* rvals, cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                         const uint32_t* sel, const uint32_t* n_sel_dev, uint32_t n_max,
-                         uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+                         const uint32_t* rkeys, const uint32_t* rvals, uint32_t n_max,
+                         cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,
                             const uint32_t* counters, size_t n_cells, cudaStream_t s,
                             LaunchCounter& lc);

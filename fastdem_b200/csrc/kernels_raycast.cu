@@ -58,71 +58,155 @@ voxel_keys_kernel(const float4* __restrict__ pm, uint32_t n, float inv, uint64_t
   vals[i] = i;
 }
 
+// Compact voxel keys.  When the crop filters bound the kept points to a box the host can
+// compute (finite range_max; see voxel_box() in capi.cu), the same [z][y][x] order fits a
+// 32-bit key: (iz - z0) << (bx+by) | (iy - y0) << bx | (ix - x0).  Subtracting a constant per
+// axis preserves the lexicographic order of voxel::pack, so the sorted sequence — and with
+// it every voxel's `start` rank — is identical to the 63-bit key's; the radix sort then
+// needs 4 passes over 8-byte pairs instead of 8 passes over 12-byte pairs.
+__global__ void __launch_bounds__(kBlock)
+voxel_keys32_kernel(const float4* __restrict__ pm, uint32_t n, float inv, const VoxelBox box,
+                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                    uint32_t* __restrict__ counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = __ldg(&pm[i]);
+  const bool ok = isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+  uint32_t key = box.invalid_key;
+  if (ok) {
+    constexpr int32_t OFF = 1 << 20;
+    int32_t ix = static_cast<int32_t>(floorf(q.x * inv));
+    int32_t iy = static_cast<int32_t>(floorf(q.y * inv));
+    int32_t iz = static_cast<int32_t>(floorf(q.z * inv));
+    ix = min(max(ix, -OFF), OFF - 1) - box.x0;
+    iy = min(max(iy, -OFF), OFF - 1) - box.y0;
+    iz = min(max(iz, -OFF), OFF - 1) - box.z0;
+    const int32_t mx = (1 << box.bx) - 1, my = (1 << box.by) - 1, mz = (1 << box.bz) - 1;
+    if (ix < 0 || ix > mx || iy < 0 || iy > my || iz < 0 || iz > mz) {
+      // cannot happen while the transforms are rigid; counted so a test / caller can see it
+      atomicAdd(&counters[CNT_VOX_VIOLATION], 1u);
+      ix = min(max(ix, 0), mx); iy = min(max(iy, 0), my); iz = min(max(iz, 0), mz);
+    }
+    key = (static_cast<uint32_t>(iz) << (box.bx + box.by)) | (static_cast<uint32_t>(iy) << box.bx) |
+          static_cast<uint32_t>(ix);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
 // one representative per voxel: idx[start + (count*7 + start*13) % count]  (:171-172).
 // The sort is stable, so within a voxel the indices ascend — the oracle's tie definition.
+template <typename Key>
 __global__ void __launch_bounds__(kBlock)
-voxel_select_kernel(const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
-                    uint32_t n, uint32_t* __restrict__ counters, uint32_t* __restrict__ out_sel) {
+voxel_select_kernel(const Key* __restrict__ skeys, const uint32_t* __restrict__ svals, uint32_t n,
+                    const Key invalid, uint32_t* __restrict__ counters,
+                    uint32_t* __restrict__ out_sel) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool head = false;
   if (i < n) {
-    const uint64_t key = skeys[i];
-    head = key != kInvalidVoxel && (i == 0 || skeys[i - 1] != key);
+    const Key key = skeys[i];
+    head = key != invalid && (i == 0 || skeys[i - 1] != key);
     uint32_t sel = kNoSel;
     if (head) {
-      // upper bound of `key` in skeys[i, n)
-      uint32_t lo = i + 1, hi = n;
-      while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (skeys[mid] == key) lo = mid + 1; else hi = mid;
+      // end of the run of `key`: voxels hold a point or two, so walk a few elements first
+      // (coalesced with the neighbours' walks) and binary-search only a long run
+      uint32_t lo = i + 1;
+      constexpr uint32_t kWalk = 6;
+      const uint32_t wend = min(n, i + 1 + kWalk);
+      while (lo < wend && skeys[lo] == key) ++lo;
+      if (lo == wend && lo < n && skeys[lo] == key) {
+        uint32_t hi = n;
+        ++lo;
+        while (lo < hi) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          if (skeys[mid] == key) lo = mid + 1; else hi = mid;
+        }
       }
       const uint64_t count = lo - i;
       const uint64_t start = i;
-      sel = svals[start + (count * 7ull + start * 13ull) % count];
+      // (count*7 + start*13) % count; a voxel with one point needs no 64-bit division
+      sel = svals[count == 1 ? start : start + (count * 7ull + start * 13ull) % count];
     }
     out_sel[i] = sel;
   }
-  const uint32_t w = __popc(__ballot_sync(0xffffffffu, head));
-  if ((threadIdx.x & 31) == 0 && w) atomicAdd(&counters[CNT_VOXELS], w);
+  // one atomic per CTA: thousands of same-address atomics would serialise in L2
+  const int heads = __syncthreads_count(head);
+  if (threadIdx.x == 0 && heads) atomicAdd(&counters[CNT_VOXELS], static_cast<uint32_t>(heads));
 }
 
-// processScan (raycasting.cpp:150-179): one thread per ray_scan point
+// ── ray ordering.  Rays are handed to the DDA kernel sorted by length: a warp then holds 32
+// rays that finish together (no lanes idling while one long ray finishes, no lanes lost to
+// untraced entries).  The order has no effect on the result — every cell keeps the MINIMUM
+// over the rays that cross it. ──
+constexpr uint32_t kRayInvalid = 0xffu;
+constexpr int kRayKeyBits = 8;
+
+// processScan's per-point part (raycasting.cpp:160-174): the observed-evidence hit of every
+// ray_scan point, and the sort key of the points that get traced
 __global__ void __launch_bounds__(kBlock)
-raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
-                    const float4* __restrict__ pts, const uint32_t* __restrict__ sel,
-                    uint32_t n_max, uint32_t* __restrict__ counters) {
+ray_keys_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
+                const float4* __restrict__ pts, const uint32_t* __restrict__ sel, uint32_t n_max,
+                uint32_t* __restrict__ counters, uint32_t* __restrict__ rkeys,
+                uint32_t* __restrict__ rvals) {
   const GridGeom g = st->geom;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   // preconditions (raycasting.cpp:230-234): sensor origin must be inside the map
   if (!geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]))) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_RC_SKIP] = 1;
+    if (i == 0) counters[CNT_RC_SKIP] = 1;
+    if (i < n_max) rkeys[i] = kRayInvalid;
     return;
   }
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_max) return;
+  uint32_t key = kRayInvalid;
   uint32_t src = i;
-  if (sel) {
-    src = sel[i];
-    if (src == kNoSel) return;
-  }
-  const float4 pt = __ldg(&pts[src]);
-  const int nrows = g.rows, ncols = g.cols;
-
-  // observed evidence: count hits per cell; the log-odds update itself is applied once
-  // per hit, in order, by the resolve kernel (:162-170)
-  {
+  if (sel) src = sel[i];
+  if (src != kNoSel) {
+    const float4 pt = __ldg(&pts[src]);
+    // observed evidence: count hits per cell; the log-odds update itself is applied once
+    // per hit, in order, by the resolve kernel (:162-170)
     int32_t row, col;
     if (geom_get_index(g, static_cast<double>(pt.x), static_cast<double>(pt.y), row, col))
-      atomicAdd(&p.hits[static_cast<size_t>(col) * nrows + row], 1u);
+      atomicAdd(&p.hits[static_cast<size_t>(col) * g.rows + row], 1u);
+    const float dx = pt.x - p.origin[0];
+    const float dy = pt.y - p.origin[1];
+    const float ray_len_2d = sqrtf(dx * dx + dy * dy);
+    // upward rays are skipped (:173); rays shorter than 1e-4 m in xy are skipped (:52-53)
+    if (pt.z < p.origin[2] && ray_len_2d >= 1e-4f) {
+      // grouping only (no exactness needed): ray length in 4-cell bins, 8 bits = one radix pass
+      const int len_cells = static_cast<int>(ray_len_2d / static_cast<float>(g.res));
+      key = static_cast<uint32_t>(min(len_cells >> 2, 254));
+    }
   }
-  if (pt.z >= p.origin[2]) return;  // skip upward rays (:173)
+  rkeys[i] = key;
+  rvals[i] = src;
+}
 
-  // traceRay (raycasting.cpp:46-139), float32 grid math
+constexpr int kRayBatch = 8;
+
+// traceRay (raycasting.cpp:46-139): one thread per traced ray, rays sorted by length so that
+// a warp's 32 rays finish together (in input order two thirds of the lanes idle: untraced
+// entries, and short rays waiting for the longest one).
+// Measured alternatives (B200, config 4, 1.05 M points; this kernel: 260 us):
+//   input order, one cell per round trip                       540 us
+//   (azimuth sector, length) order: loads coalesce (2 sectors per request instead of ~30)
+//     but lanes in lockstep on the same cells all see the same stale minimum and all
+//     fire: 24 M atomics instead of 6 M                          355 us
+//   the same + per-CTA shared-memory hash table of the wedge's minima, one flush per
+//     cell: same-address shared atomics and probe chains          1280 us
+__global__ void __launch_bounds__(kBlock)
+raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
+                    const float4* __restrict__ pts, const uint32_t* __restrict__ rkeys,
+                    const uint32_t* __restrict__ rvals, uint32_t n_max) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max) return;
+  if (rkeys[i] == kRayInvalid) return;  // sorted last: whole warps leave here
+  const GridGeom g = st->geom;
+  const float4 pt = __ldg(&pts[rvals[i]]);
+  const int nrows = g.rows, ncols = g.cols;
   const float resolution = static_cast<float>(g.res);
   const float sx = p.origin[0], sy = p.origin[1], sz = p.origin[2];
   const float dx = pt.x - sx;
   const float dy = pt.y - sy;
-  const float ray_len_2d = sqrtf(dx * dx + dy * dy);
-  if (ray_len_2d < 1e-4f) return;
   const float dz = pt.z - sz;
   const float origin_x = static_cast<float>(g.pos[0]) + nrows * resolution * 0.5f;
   const float origin_y = static_cast<float>(g.pos[1]) + ncols * resolution * 0.5f;
@@ -157,38 +241,55 @@ raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* 
     t_delta_c = 1e30f;
   }
   const int max_steps = nrows + ncols;
-  // The sensor cell is inside the map (precondition above) and the map is convex, so once
-  // the ray has left the map it never comes back: the reference keeps stepping (its cells
-  // fail the bounds test and are ignored); stopping there changes nothing but the work.
+  const int start_r = g.start[0], start_c = g.start[1];
+  // The DDA is run kRayBatch cells at a time: first the batch's cells and exit heights
+  // (pure arithmetic), then ALL their loads back to back, then the compares / atomics.  The
+  // loads are independent, so one memory round trip is paid per batch instead of per cell.
   bool was_inside = false;
-  for (int s = 0; s < max_steps; ++s) {
-    if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
-      was_inside = true;
-      int mr = r + g.start[0];  // == (r + start) % size: both terms are in [0, size)
-      if (mr >= nrows) mr -= nrows;
-      int mc = c + g.start[1];
-      if (mc >= ncols) mc -= ncols;
-      const float t_exit = fminf(t_max_r, t_max_c);
-      const float height = sz + fminf(t_exit, 1.0f) * dz;
-      // Every ray starts in the sensor's cell, so the cells around it would take one atomic
-      // per ray.  A minimum only ever decreases: if the value already stored (even a stale,
-      // cached one — it can only be larger than the true current value) is <= mine, my
-      // update cannot change anything and the atomic is skipped.
-      uint32_t* slot = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
-      const uint32_t e = enc_f32(height);
-      if (e < *slot) atomicMin(slot, e);  // plain (L1-cacheable) load: staleness is safe here
-    } else if (was_inside) {
-      break;
+  bool done = false;
+  int s = 0;
+  while (!done) {
+    uint32_t* sl[kRayBatch];
+    uint32_t ev[kRayBatch];
+    uint32_t cv[kRayBatch];
+#pragma unroll
+    for (int k = 0; k < kRayBatch; ++k) {
+      sl[k] = nullptr;
+      ev[k] = 0u;
+      if (done) continue;
+      if (s >= max_steps) { done = true; continue; }
+      if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
+        was_inside = true;
+        int mr = r + start_r;  // == (r + start) % size: both terms are in [0, size)
+        if (mr >= nrows) mr -= nrows;
+        int mc = c + start_c;
+        if (mc >= ncols) mc -= ncols;
+        sl[k] = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
+        const float t_exit = fminf(t_max_r, t_max_c);
+        ev[k] = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
+      } else if (was_inside) {
+        // the map is convex and the sensor cell is inside: once out, the ray never comes
+        // back (the reference keeps stepping over cells that fail its bounds test)
+        done = true;
+        continue;
+      }
+      if (t_max_r < t_max_c) {
+        if (t_max_r >= 1.0f) done = true;
+        else { r += step_r; t_max_r += t_delta_r; }
+      } else {
+        if (t_max_c >= 1.0f) done = true;
+        else { c += step_c; t_max_c += t_delta_c; }
+      }
+      ++s;
     }
-    if (t_max_r < t_max_c) {
-      if (t_max_r >= 1.0f) break;
-      r += step_r;
-      t_max_r += t_delta_r;
-    } else {
-      if (t_max_c >= 1.0f) break;
-      c += step_c;
-      t_max_c += t_delta_c;
-    }
+    // Plain (L1-cacheable) loads: a minimum only ever decreases, so a stale value can only
+    // be LARGER than the true one — the atomic is then issued needlessly, never skipped
+    // wrongly.
+#pragma unroll
+    for (int k = 0; k < kRayBatch; ++k) cv[k] = sl[k] ? *sl[k] : 0u;
+#pragma unroll
+    for (int k = 0; k < kRayBatch; ++k)
+      if (sl[k] && ev[k] < cv[k]) atomicMin(sl[k], ev[k]);
   }
 }
 
@@ -346,19 +447,43 @@ void launch_voxel_keys(const float4* pm, uint32_t n, float inv_voxel, uint64_t* 
   voxel_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(pm, n, inv_voxel, keys, vals);
   ++lc.mine;
 }
+void launch_voxel_keys32(const float4* pm, uint32_t n, float inv_voxel, const VoxelBox& box,
+                         uint32_t* keys, uint32_t* vals, uint32_t* counters, cudaStream_t s,
+                         LaunchCounter& lc) {
+  if (n == 0) return;
+  voxel_keys32_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(pm, n, inv_voxel, box, keys, vals,
+                                                                   counters);
+  ++lc.mine;
+}
 void launch_voxel_select(const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
                          uint32_t* counters, uint32_t* out_sel, cudaStream_t s, LaunchCounter& lc) {
   if (n == 0) return;
-  voxel_select_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(sorted_keys, sorted_vals, n,
-                                                                  counters, out_sel);
+  voxel_select_kernel<uint64_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(
+      sorted_keys, sorted_vals, n, kInvalidVoxel, counters, out_sel);
+  ++lc.mine;
+}
+void launch_voxel_select32(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                           uint32_t invalid_key, uint32_t* counters, uint32_t* out_sel,
+                           cudaStream_t s, LaunchCounter& lc) {
+  if (n == 0) return;
+  voxel_select_kernel<uint32_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(
+      sorted_keys, sorted_vals, n, invalid_key, counters, out_sel);
+  ++lc.mine;
+}
+int ray_key_bits() { return kRayKeyBits; }
+void launch_ray_keys(const RaycastParams& p, const DeviceState* st, const float4* pts,
+                     const uint32_t* sel, uint32_t n_max, uint32_t* counters, uint32_t* rkeys,
+                     uint32_t* rvals, cudaStream_t s, LaunchCounter& lc) {
+  if (n_max == 0) return;
+  ray_keys_kernel<<<(n_max + kBlock - 1) / kBlock, kBlock, 0, s>>>(p, st, pts, sel, n_max, counters,
+                                                                  rkeys, rvals);
   ++lc.mine;
 }
 void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                         const uint32_t* sel, const uint32_t* /*n_sel_dev*/, uint32_t n_max,
-                         uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+                         const uint32_t* rkeys, const uint32_t* rvals, uint32_t n_max,
+                         cudaStream_t s, LaunchCounter& lc) {
   if (n_max == 0) return;
-  raycast_scan_kernel<<<(n_max + kBlock - 1) / kBlock, kBlock, 0, s>>>(p, st, pts, sel, n_max,
-                                                                      counters);
+  raycast_scan_kernel<<<(n_max + kBlock - 1) / kBlock, kBlock, 0, s>>>(p, st, pts, rkeys, rvals, n_max);
   ++lc.mine;
 }
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* /*st*/,

@@ -100,7 +100,8 @@ typedef struct fdem_scan_stats {
   int64_t n_cells;  /* cells touched by rasterize (elevation_mapping.cpp:41-92)  */
   int64_t n_voxels; /* ray_scan size after voxelGrid(ANY) (fastdem.cpp:156-157)  */
   int32_t integrated;
-  int32_t _pad;
+  int32_t voxel_box_violations; /* raycasting self-check: points outside the key box the
+                                   host predicted from the crop filters; always 0 */
 } fdem_scan_stats;
 
 /* nanogrid::GridMap geometry accessors (getSize/getResolution/getLength/getPosition/

@@ -65,6 +65,7 @@ def test_c4_oracle_parity_with_raycasting(fdem):
     wl = syn.WORKLOADS["c4_dense_raycast"]
     gmap, omap, gdem, odem, gs, os_ = run_pair(fdem, wl, 2)
     assert gs[-1].n_voxels > 100000 and gs[-1].n_cells > 50000
+    assert all(s.voxel_box_violations == 0 for s in gs)
     compare_maps(gmap, omap)
 
 

@@ -560,6 +560,38 @@ def test_integrate_with_raycasting_matches_oracle(fdem):
     compare_maps(g, o)
 
 
+def test_voxel_compact_keys_match_the_63bit_keys(fdem):
+    """voxelGrid(ANY) sorts 32-bit box-relative keys when the crop filters bound the kept
+    points (finite range_max) and the reference's 63-bit keys otherwise; both must pick the
+    same representatives, i.e. produce the same map — with a tilted, translated robot pose so
+    all three box axes are exercised."""
+    from fastdem_b200 import synthetic as syn
+    wl = syn.WORKLOADS["tiny"]
+    maps = []
+    for range_max in (20.0, 3.0e6):   # 3e6 > voxel_box()'s limit -> 63-bit path; no point is that far
+        cfg = wl.config()
+        cfg.raycasting_enabled = 1
+        cfg.range_max = range_max
+        g = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution)
+        o = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+        gd, od = fdem.FastDEM(g, cfg), ob.OracleFastDEM(o, cfg)
+        for k in range(5):
+            s = syn.make_scan(wl, k)
+            Twb = np.array(s["T_world_base"], dtype=np.float64).copy()
+            a = 0.03 * (k + 1)   # small roll: z of the map frame mixes with y of the base frame
+            Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+            Twb[:3, :3] = Twb[:3, :3] @ Rx
+            Twb[:3, 3] += (137.0, -61.5, 0.0)   # far from the origin: box corner offsets matter
+            st = gd.integrate_stats(fdem.PointCloud(s["xyzw"], s["intensity"]), s["T_base_sensor"], Twb)
+            ok, ost, _ = od.integrate(s["xyzw"], s["T_base_sensor"], Twb, s["intensity"])
+            assert st.n_voxels == ost.n_voxels and st.n_cells == ost.n_cells and st.n_voxels > 100
+            assert st.voxel_box_violations == 0
+        compare_maps(g, o)
+        maps.append({n: g.get(n) for n in ("elevation", "raycasting", "_visibility_logodds")})
+    for n in maps[0]:
+        assert np.array_equal(maps[0][n], maps[1][n], equal_nan=True), n
+
+
 def test_inpainting_matches_oracle(fdem):  # test_postprocess.cpp:41-69
     rng = np.random.RandomState(9)
     g = fdem.ElevationMap(10.0, 10.0, 0.5)
