@@ -8,7 +8,8 @@ from .capi import (EST_KALMAN, EST_P2QUANTILE, MODE_GLOBAL, MODE_LOCAL, MOVE_CLE
                    MOVE_CLEAR_BASIC_LAYERS, SENSOR_CONSTANT, SENSOR_LIDAR, SENSOR_RGBD, FdemConfig,
                    FdemError, FdemGeometry, FdemScanStats, default_config, load_library)
 from .api import (Config, ElevationMap, ElevationMapping, EstimationType, FastDEM, MappingMode,
-                  PointCloud, PointCloud2, SensorType, applyInpainting, applyRaycasting, applySpatialSmoothing, layer, voxelGridAny)
+                  PointCloud, PointCloud2, SensorType, applyFeatureExtraction, applyInpainting, applyRaycasting, applySpatialSmoothing,
+                  applyUncertaintyFusion, layer, voxelGridAny)
 
 from . import io_npz as io  # fastdem::io::{saveNpz, loadNpz}
 from .config_yaml import loadConfig, parseConfig
@@ -16,7 +17,8 @@ from .config_yaml import loadConfig, parseConfig
 __all__ = [
     "io", "loadConfig", "parseConfig",
     "Config", "ElevationMap", "ElevationMapping", "EstimationType", "FastDEM", "MappingMode",
-    "PointCloud", "PointCloud2", "SensorType", "applyInpainting", "applyRaycasting", "applySpatialSmoothing", "layer", "voxelGridAny",
+    "PointCloud", "PointCloud2", "SensorType", "applyFeatureExtraction", "applyInpainting", "applyRaycasting",
+    "applySpatialSmoothing", "applyUncertaintyFusion", "layer", "voxelGridAny",
     "FdemConfig", "FdemError", "FdemGeometry", "FdemScanStats", "default_config", "load_library",
 ]
 __version__ = "0.1.0"

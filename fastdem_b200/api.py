@@ -766,3 +766,24 @@ def applySpatialSmoothing(map: ElevationMap, layer_name: str, kernel_size: int =
     """fastdem::applySpatialSmoothing (postprocess/spatial_smoothing.hpp:38-67)."""
     lib = capi.load_library()
     check(lib.fdem_spatial_smoothing(map.handle, layer_name.encode(), kernel_size, min_valid_neighbors))
+
+
+def applyUncertaintyFusion(map: ElevationMap, search_radius: float = 0.15, spatial_sigma: float = 0.05,
+                           quantile_lower: float = 0.01, quantile_upper: float = 0.99,
+                           min_valid_neighbors: int = 3, enabled: bool = True) -> None:
+    """fastdem::applyUncertaintyFusion(map, config::UncertaintyFusion)
+    (src/uncertainty_fusion.cpp:103-186); keyword defaults = config/postprocess.hpp:33-40
+    except `enabled` (the reference's config defaults to disabled = no-op)."""
+    if not enabled:
+        return
+    lib = capi.load_library()
+    check(lib.fdem_uncertainty_fusion(map.handle, search_radius, spatial_sigma, quantile_lower,
+                                      quantile_upper, min_valid_neighbors))
+
+
+def applyFeatureExtraction(map: ElevationMap, analysis_radius: float = 0.3, min_valid_neighbors: int = 4,
+                           step_lower_percentile: float = 0.05, step_upper_percentile: float = 0.95) -> None:
+    """fastdem::applyFeatureExtraction (src/feature_extraction.cpp:28-118)."""
+    lib = capi.load_library()
+    check(lib.fdem_feature_extraction(map.handle, analysis_radius, min_valid_neighbors,
+                                      step_lower_percentile, step_upper_percentile))

@@ -122,6 +122,8 @@ SIGNATURES = {
     "fdem_voxel_grid_any": (_ST, [_P, _f32p, C.c_size_t, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]),
     "fdem_inpaint": (_ST, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "fdem_spatial_smoothing": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32]),
+    "fdem_uncertainty_fusion": (_ST, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
+    "fdem_feature_extraction": (_ST, [_P, C.c_float, C.c_int32, C.c_float, C.c_float]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),

@@ -251,6 +251,14 @@ void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const
                             LaunchCounter& lc);
 int launch_median_filter(const float* src, float* dst, const DeviceState* st, int kernel_size,
                          int min_valid, cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
+// returns 1 when radius / resolution exceeds the compiled neighbourhood (5 cells)
+int launch_uncertainty_fusion(const float* upper_in, const float* lower_in, float* upper_out,
+                              float* lower_out, const DeviceState* st, float radius, double res,
+                              float spatial_sigma, float q_lower, float q_upper, int min_valid,
+                              cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
+int launch_feature_extraction(const float* elev, float* const out7[7], const DeviceState* st,
+                              float radius, double res, int min_valid, float p_lo, float p_hi,
+                              cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 

@@ -432,6 +432,309 @@ median_filter_kernel(const float* __restrict__ src, float* __restrict__ dst,
   }
 }
 
+// ── circular neighbourhoods: nanogrid region(radius) / neighbors() are not in the reference
+// tree (un-vendored nanoGrid), so they are restated from the call sites:
+// offsets with (float)((dr^2+dc^2) res^2) <= radius^2, centre included, dr outer / dc inner,
+// restricted to in-bounds LOGICAL cells ──
+constexpr int kMaxRegionHalf = 5;
+constexpr int kMaxRegionCells = (2 * kMaxRegionHalf + 1) * (2 * kMaxRegionHalf + 1);  // 121
+
+// weighted quantile of samples already sorted by value (SimpleWeightedECDF::quantile,
+// uncertainty_fusion.cpp:62-90)
+__device__ __forceinline__ float weighted_quantile(const float* v, const float* w, int n, float p) {
+  if (n == 0) return nanf_();
+  if (n == 1) return v[0];
+  float total = 0.0f;
+  for (int k = 0; k < n; ++k) total += w[k];
+  if (total <= 0.0f) return nanf_();
+  const float target = p * total;
+  float cumulative = 0.0f;
+  for (int k = 0; k < n; ++k) {
+    cumulative += w[k];
+    if (cumulative >= target) return v[k];
+  }
+  return v[n - 1];
+}
+
+// stable insertion of (val, wt) into arrays sorted by val
+__device__ __forceinline__ void sorted_insert(float* v, float* w, int n, float val, float wt) {
+  int j = n;
+  while (j > 0 && val < v[j - 1]) {
+    v[j] = v[j - 1];
+    w[j] = w[j - 1];
+    --j;
+  }
+  v[j] = val;
+  w[j] = wt;
+}
+
+// applyUncertaintyFusion (fastdem/src/uncertainty_fusion.cpp:103-186): bilateral weights
+// (Gaussian in distance x inverse bound range) -> weighted quantiles of the neighbours'
+// lower / upper bounds.  Reads the snapshots, writes the layers (double buffer).
+__global__ void __launch_bounds__(128)
+uncertainty_fusion_kernel(const float* __restrict__ upper_in, const float* __restrict__ lower_in,
+                          float* __restrict__ upper_out, float* __restrict__ lower_out,
+                          const DeviceState* __restrict__ st, int half, float radius_sq,
+                          float inv_2sigma_sq, float q_lower, float q_upper, int min_valid,
+                          int rows_local, int cols) {
+  const GridGeom g = st->geom;
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float cu = upper_in[i], cl = lower_in[i];
+  if (!isfinite(cu) || !isfinite(cl)) return;
+  const int bc = static_cast<int>(i / rows_local);
+  const int br = static_cast<int>(i - static_cast<size_t>(bc) * rows_local);
+  const int lr = wrap_index(br - g.start[0] + g.rows, g.rows);
+  const int lc = wrap_index(bc - g.start[1] + g.cols, g.cols);
+  float lo_v[kMaxRegionCells], lo_w[kMaxRegionCells], up_v[kMaxRegionCells], up_w[kMaxRegionCells];
+  int ns = 0, valid = 0;
+  const double res2 = g.res * g.res;
+  for (int dr = -half; dr <= half; ++dr) {
+    for (int dc = -half; dc <= half; ++dc) {
+      const float dist_sq = static_cast<float>(static_cast<double>(dr * dr + dc * dc) * res2);
+      if (!(dist_sq <= radius_sq)) continue;
+      const int nr = lr + dr, nc = lc + dc;
+      if (nr < 0 || nr >= g.rows || nc < 0 || nc >= g.cols) continue;
+      const size_t nl = static_cast<size_t>(wrap_index(nc + g.start[1], g.cols)) * rows_local +
+                        wrap_index(nr + g.start[0], g.rows);
+      const float nu = upper_in[nl], nlo = lower_in[nl];
+      if (!isfinite(nu) || !isfinite(nlo)) continue;
+      const float w_spatial = expf(-dist_sq * inv_2sigma_sq);
+      const float range = nu - nlo;
+      const float w_range = 1.0f / (range + 1e-4f);
+      const float w = w_spatial * w_range;
+      if (w > 1e-6f) {
+        sorted_insert(lo_v, lo_w, ns, nlo, w);
+        sorted_insert(up_v, up_w, ns, nu, w);
+        ++ns;
+      }
+      ++valid;
+    }
+  }
+  if (valid >= min_valid) {
+    const float lower = weighted_quantile(lo_v, lo_w, ns, q_lower);
+    const float upper = weighted_quantile(up_v, up_w, ns, q_upper);
+    if (isfinite(lower) && isfinite(upper)) {
+      upper_out[i] = upper;
+      lower_out[i] = lower;
+    }
+  }
+}
+
+// ── 3x3 symmetric eigen-decomposition, the closed form Eigen's
+// SelfAdjointEigenSolver<Matrix3f>::computeDirect uses (nanopcl::geometry::computePCA,
+// nanopcl/geometry/impl/pca.hpp:67-90): shift by trace/3, scale to [-1,1], trigonometric
+// roots, eigenvectors from row cross products. ──
+struct Eig3 {
+  float val[3];
+  float vec[3][3];
+};
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float sqnorm3v(const float* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
+__device__ __forceinline__ void eig3_kernel(const float m[3][3], float* res, float* representative) {
+  int i0 = 0;
+  float best = fabsf(m[0][0]);
+#pragma unroll
+  for (int i = 1; i < 3; ++i)
+    if (fabsf(m[i][i]) > best) { best = fabsf(m[i][i]); i0 = i; }
+  float c0[3], c1[3], a[3], b[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    representative[i] = (i0 == 0) ? m[i][0] : (i0 == 1) ? m[i][1] : m[i][2];
+    a[i] = (i0 == 0) ? m[i][1] : (i0 == 1) ? m[i][2] : m[i][0];  // column (i0+1)%3
+    b[i] = (i0 == 0) ? m[i][2] : (i0 == 1) ? m[i][0] : m[i][1];  // column (i0+2)%3
+  }
+  cross3(representative, a, c0);
+  cross3(representative, b, c1);
+  const float n0 = sqnorm3v(c0), n1 = sqnorm3v(c1);
+  if (n0 > n1) {
+    const float s = sqrtf(n0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) res[i] = c0[i] / s;
+  } else {
+    const float s = sqrtf(n1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) res[i] = c1[i] / s;
+  }
+}
+__device__ __forceinline__ Eig3 eig3_direct(const float cov[3][3]) {
+  Eig3 out;
+  constexpr float eps = 1.1920929e-07f;
+  const float shift = (cov[0][0] + cov[1][1] + cov[2][2]) / 3.0f;
+  float m[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) m[i][j] = (i >= j) ? cov[i][j] : cov[j][i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) m[i][i] -= shift;
+  float scale = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) scale = fmaxf(scale, fabsf(m[i][j]));
+  if (scale > 0.0f) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) m[i][j] /= scale;
+  }
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[1][0] * m[2][0] * m[2][1] -
+                   m[0][0] * m[2][1] * m[2][1] - m[1][1] * m[2][0] * m[2][0] - m[2][2] * m[1][0] * m[1][0];
+  const float c1 = m[0][0] * m[1][1] - m[1][0] * m[1][0] + m[0][0] * m[2][2] - m[2][0] * m[2][0] +
+                   m[1][1] * m[2][2] - m[2][1] * m[2][1];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  const float inv3 = 1.0f / 3.0f, sqrt3 = sqrtf(3.0f);
+  const float c2_3 = c2 * inv3;
+  float a_3 = (c2 * c2_3 - c1) * inv3;
+  a_3 = fmaxf(a_3, 0.0f);
+  const float half_b = 0.5f * (c0 + c2_3 * (2.0f * c2_3 * c2_3 - c1));
+  float q = a_3 * a_3 * a_3 - half_b * half_b;
+  q = fmaxf(q, 0.0f);
+  const float rho = sqrtf(a_3);
+  const float theta = atan2f(sqrtf(q), half_b) * inv3;
+  const float ct = cosf(theta), sn = sinf(theta);
+  float ev[3] = {c2_3 - rho * (ct + sqrt3 * sn), c2_3 - rho * (ct - sqrt3 * sn), c2_3 + 2.0f * rho * ct};
+  float V0[3] = {1, 0, 0}, V1[3] = {0, 1, 0}, V2[3] = {0, 0, 1};
+  if (!((ev[2] - ev[0]) <= eps)) {
+    float d0 = ev[2] - ev[1];
+    const float d1 = ev[1] - ev[0];
+    const bool swapped = d0 > d1;  // Eigen: swap(k, l); d0 = d1;
+    if (swapped) d0 = d1;
+    float* Vk = swapped ? V2 : V0;
+    float* Vl = swapped ? V0 : V2;
+    const float ek = swapped ? ev[2] : ev[0];
+    const float el = swapped ? ev[0] : ev[2];
+    float tmp[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tmp[i][j] = m[i][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tmp[i][i] -= ek;
+    eig3_kernel(tmp, Vk, Vl);
+    if (d0 <= 2.0f * eps * d1) {
+      const float dot = Vk[0] * Vl[0] + Vk[1] * Vl[1] + Vk[2] * Vl[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Vl[i] -= dot * Vl[i];
+      const float nrm = sqrtf(sqnorm3v(Vl));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Vl[i] /= nrm;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tmp[i][j] = m[i][j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tmp[i][i] -= el;
+      float dummy[3];
+      eig3_kernel(tmp, Vl, dummy);
+    }
+    float c[3];
+    cross3(V2, V0, c);
+    const float nrm = sqrtf(sqnorm3v(c));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) V1[i] = c[i] / nrm;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out.val[k] = ev[k] * scale + shift;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    out.vec[0][i] = V0[i];
+    out.vec[1][i] = V1[i];
+    out.vec[2][i] = V2[i];
+  }
+  return out;
+}
+
+struct FeatureLayers {
+  float *step, *slope, *roughness, *curvature, *nx, *ny, *nz;
+};
+
+// applyFeatureExtraction (fastdem/src/feature_extraction.cpp:28-118): local PCA of the
+// elevation patch -> normal, slope, roughness, curvature; percentile range -> step
+__global__ void __launch_bounds__(128)
+feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers out,
+                          const DeviceState* __restrict__ st, int half, float radius_sq,
+                          int min_valid, float p_lo, float p_hi, int rows_local, int cols) {
+  const GridGeom g = st->geom;
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float center_z = elev[i];
+  if (!isfinite(center_z)) return;
+  const int bc = static_cast<int>(i / rows_local);
+  const int br = static_cast<int>(i - static_cast<size_t>(bc) * rows_local);
+  const int lr = wrap_index(br - g.start[0] + g.rows, g.rows);
+  const int lc = wrap_index(bc - g.start[1] + g.cols, g.cols);
+  const float resf = static_cast<float>(g.res);
+  const double res2 = g.res * g.res;
+  float sum[3] = {0.0f, 0.0f, 0.0f};
+  float sq[3][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+  float z_vals[kMaxRegionCells];
+  int count = 0;
+  for (int dr = -half; dr <= half; ++dr) {
+    for (int dc = -half; dc <= half; ++dc) {
+      const float dist_sq = static_cast<float>(static_cast<double>(dr * dr + dc * dc) * res2);
+      if (!(dist_sq <= radius_sq)) continue;
+      const int nr = lr + dr, nc = lc + dc;
+      if (nr < 0 || nr >= g.rows || nc < 0 || nc >= g.cols) continue;
+      const float nz = elev[static_cast<size_t>(wrap_index(nc + g.start[1], g.cols)) * rows_local +
+                            wrap_index(nr + g.start[0], g.rows)];
+      if (!isfinite(nz)) continue;
+      // world-frame displacement (grid_map: row -> -x, col -> -y)
+      const float d[3] = {-dr * resf, -dc * resf, nz - center_z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) sum[a] += d[a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) sq[a][b] += d[a] * d[b];
+      // keep z_vals sorted (the reference sorts afterwards; same multiset)
+      int j = count;
+      while (j > 0 && nz < z_vals[j - 1]) {
+        z_vals[j] = z_vals[j - 1];
+        --j;
+      }
+      z_vals[j] = nz;
+      ++count;
+    }
+  }
+  if (count < min_valid) return;
+  const float inv_n = 1.0f / static_cast<float>(count);
+  float mean[3], cov[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) mean[a] = sum[a] * inv_n;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) cov[a][b] = sq[a][b] * inv_n - mean[a] * mean[b];
+  const float trace = cov[0][0] + cov[1][1] + cov[2][2];
+  if (trace < 1.1920929e-07f) return;  // computePCA: degenerate covariance -> invalid
+  const Eig3 pca = eig3_direct(cov);
+  if (pca.val[1] < 1e-8f) return;      // collinear patch
+  float normal[3] = {pca.vec[0][0], pca.vec[0][1], pca.vec[0][2]};
+  if (normal[2] < 0.0f) {
+    normal[0] = -normal[0];
+    normal[1] = -normal[1];
+    normal[2] = -normal[2];
+  }
+  const int lo = static_cast<int>(p_lo * (count - 1));
+  const int hi = static_cast<int>(p_hi * (count - 1));
+  out.step[i] = z_vals[hi] - z_vals[lo];
+  out.slope[i] = acosf(fabsf(normal[2])) * 180.0f / 3.14159265358979323846f;
+  out.roughness[i] = sqrtf(pca.val[0]);
+  out.curvature[i] = (trace > 0.0f) ? fabsf(pca.val[0] / trace) : 0.0f;
+  out.nx[i] = normal[0];
+  out.ny[i] = normal[1];
+  out.nz[i] = normal[2];
+}
+
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 8) {
   size_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
@@ -502,6 +805,33 @@ int launch_median_filter(const float* src, float* dst, const DeviceState* st, in
     case 7: median_filter_kernel<7><<<grid, kBlock, 0, s>>>(src, dst, st, min_valid, rows_local, cols); break;
     default: return 1;
   }
+  ++lc.mine;
+  return 0;
+}
+int launch_uncertainty_fusion(const float* upper_in, const float* lower_in, float* upper_out,
+                              float* lower_out, const DeviceState* st, float radius, double res,
+                              float spatial_sigma, float q_lower, float q_upper, int min_valid,
+                              cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {
+  const int half = static_cast<int>(ceil(static_cast<double>(radius) / res));
+  if (half > kMaxRegionHalf) return 1;
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  if (n == 0) return 0;
+  uncertainty_fusion_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(
+      upper_in, lower_in, upper_out, lower_out, st, half, radius * radius,
+      1.0f / (2.0f * spatial_sigma * spatial_sigma), q_lower, q_upper, min_valid, rows_local, cols);
+  ++lc.mine;
+  return 0;
+}
+int launch_feature_extraction(const float* elev, float* const out7[7], const DeviceState* st,
+                              float radius, double res, int min_valid, float p_lo, float p_hi,
+                              cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {
+  const int half = static_cast<int>(ceil(static_cast<double>(radius) / res));
+  if (half > kMaxRegionHalf) return 1;
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  if (n == 0) return 0;
+  FeatureLayers fl{out7[0], out7[1], out7[2], out7[3], out7[4], out7[5], out7[6]};
+  feature_extraction_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(
+      elev, fl, st, half, radius * radius, min_valid, p_lo, p_hi, rows_local, cols);
   ++lc.mine;
   return 0;
 }

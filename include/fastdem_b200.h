@@ -288,6 +288,23 @@ fdem_status fdem_inpaint(fdem_map* map, int32_t max_iterations, int32_t min_vali
 fdem_status fdem_spatial_smoothing(fdem_map* map, const char* layer_name, int32_t kernel_size,
                                    int32_t min_valid_neighbors);
 
+/* fastdem::applyUncertaintyFusion(map, config::UncertaintyFusion)
+ * (fastdem/src/uncertainty_fusion.cpp:103-186; config/postprocess.hpp:33-40): bilateral-weighted
+ * quantiles of the neighbours' lower / upper bounds, written back to upper_bound / lower_bound.
+ * Missing bound layers are a no-op like in the reference (warn + return).  The neighbourhood
+ * (search_radius / resolution) may span at most 5 cells: FDEM_ERR_UNSUPPORTED beyond. */
+fdem_status fdem_uncertainty_fusion(fdem_map* map, float search_radius, float spatial_sigma,
+                                    float quantile_lower, float quantile_upper,
+                                    int32_t min_valid_neighbors);
+
+/* fastdem::applyFeatureExtraction(map, analysis_radius, min_valid_neighbors,
+ * step_lower_percentile, step_upper_percentile) (fastdem/src/feature_extraction.cpp:28-118):
+ * local PCA of the elevation patch -> layers step, slope, roughness, curvature, _normal_x,
+ * _normal_y, _normal_z (added NaN-filled when missing).  No elevation layer = no-op. */
+fdem_status fdem_feature_extraction(fdem_map* map, float analysis_radius,
+                                    int32_t min_valid_neighbors, float step_lower_percentile,
+                                    float step_upper_percentile);
+
 /* ── instrumentation ──────────────────────────────────────────────────────── */
 /* pipeline stages of one scan, in stream order */
 enum {

@@ -375,6 +375,13 @@ constexpr const char* ghost_removal = "ghost_removal";
 constexpr const char* raycasting = "raycasting";
 constexpr const char* visibility_logodds = "_visibility_logodds";
 constexpr const char* elevation_inpainted = "elevation_inpainted";
+constexpr const char* step = "step";
+constexpr const char* slope = "slope";
+constexpr const char* roughness = "roughness";
+constexpr const char* curvature = "curvature";
+constexpr const char* normal_x = "_normal_x";
+constexpr const char* normal_y = "_normal_y";
+constexpr const char* normal_z = "_normal_z";
 }  // namespace layer
 
 using Matrix = std::vector<float>;  // rows*cols, column-major: [c*rows + r]
@@ -1153,6 +1160,283 @@ inline void applySpatialSmoothing(ElevationMap& map, const std::string& layer_na
       const size_t mid = window.size() / 2;
       std::nth_element(window.begin(), window.begin() + mid, window.end());
       output[l] = window[mid];
+    }
+  }
+}
+
+// ───────────────────────────── circular regions ("next" rows) ────────────────
+// nanogrid::GridMap::region(radius) / neighbors(cell, region) are NOT in the tree (nanoGrid is
+// an un-vendored dependency) — PARITY UNPINNED.  Restated from the call sites: a region is a
+// list of (d_row, d_col, dist_sq [m^2]) offsets; neighbors() yields the offsets whose LOGICAL
+// cell is inside the map.  The 3x3 box region contains the centre (inpainting.cpp:45 skips it
+// by hand), so the circular one does too.  Definition used here and in the kernels: offsets
+// with dist_sq = (float)((dr^2 + dc^2) * res^2) <= radius^2, dr outer / dc inner, half-width
+// ceil(radius / res).  Pinned only loosely: a 0.6 m radius on a 0.5 m grid must reach the four
+// edge neighbours (test_postprocess.cpp:193-225: "slightly more than 1 cell").
+struct RegionEntry {
+  int dr, dc;
+  float dist_sq;
+};
+inline std::vector<RegionEntry> circularRegion(float radius, double res) {
+  std::vector<RegionEntry> out;
+  const int h = static_cast<int>(std::ceil(static_cast<double>(radius) / res));
+  const float r2 = radius * radius;
+  for (int dr = -h; dr <= h; ++dr)
+    for (int dc = -h; dc <= h; ++dc) {
+      const float d2 = static_cast<float>(static_cast<double>(dr * dr + dc * dc) * res * res);
+      if (d2 <= r2) out.push_back({dr, dc, d2});
+    }
+  return out;
+}
+
+// ───────────────────────────── uncertainty fusion ("next" row) ───────────────
+// fastdem/src/uncertainty_fusion.cpp:103-186 (+ SimpleWeightedECDF :36-97).  The reference
+// sorts the samples with std::sort (unstable): equal values may swap, which can only change
+// the float summation order of their weights; the restatement uses a stable insertion sort.
+struct UncertaintyFusionConfig {
+  bool enabled = false;
+  float search_radius = 0.15f, spatial_sigma = 0.05f, quantile_lower = 0.01f, quantile_upper = 0.99f;
+  int min_valid_neighbors = 3;
+};
+struct WeightedSample {
+  float value, weight;
+};
+inline float weightedQuantile(std::vector<WeightedSample>& s, float p) {
+  if (s.empty()) return NAN;
+  if (s.size() == 1) return s[0].value;
+  for (size_t i = 1; i < s.size(); ++i) {  // stable insertion sort by value
+    const WeightedSample v = s[i];
+    size_t j = i;
+    while (j > 0 && v.value < s[j - 1].value) {
+      s[j] = s[j - 1];
+      --j;
+    }
+    s[j] = v;
+  }
+  float total = 0.0f;
+  for (const auto& x : s) total += x.weight;
+  if (total <= 0.0f) return NAN;
+  const float target = p * total;
+  float cumulative = 0.0f;
+  for (const auto& x : s) {
+    cumulative += x.weight;
+    if (cumulative >= target) return x.value;
+  }
+  return s.back().value;
+}
+inline void applyUncertaintyFusion(ElevationMap& map, const UncertaintyFusionConfig& cfg) {
+  if (!cfg.enabled) return;
+  if (!map.exists(layer::upper_bound) || !map.exists(layer::lower_bound)) return;
+  Matrix& upper_mat = map.get(layer::upper_bound);
+  Matrix& lower_mat = map.get(layer::lower_bound);
+  const auto reg = circularRegion(cfg.search_radius, map.resolution());
+  const float inv_2sigma_sq = 1.0f / (2.0f * cfg.spatial_sigma * cfg.spatial_sigma);
+  Matrix upper_buffer = upper_mat, lower_buffer = lower_mat;
+  const int R = map.rows(), C = map.cols();
+  const Index st = map.startIndex();
+  std::vector<WeightedSample> lo, up;
+  for (int lc = 0; lc < C; ++lc) {
+    for (int lr = 0; lr < R; ++lr) {
+      const size_t l = map.lin(wrapIndex(lr + st.r, R), wrapIndex(lc + st.c, C));
+      if (!std::isfinite(upper_mat[l]) || !std::isfinite(lower_mat[l])) continue;
+      lo.clear();
+      up.clear();
+      int valid = 0;
+      for (const auto& e : reg) {
+        const int nr = lr + e.dr, nc = lc + e.dc;
+        if (nr < 0 || nr >= R || nc < 0 || nc >= C) continue;
+        const size_t nl = map.lin(wrapIndex(nr + st.r, R), wrapIndex(nc + st.c, C));
+        const float nu = upper_mat[nl], nlo = lower_mat[nl];
+        if (!std::isfinite(nu) || !std::isfinite(nlo)) continue;
+        const float w_spatial = std::exp(-e.dist_sq * inv_2sigma_sq);
+        const float range = nu - nlo;
+        const float w_range = 1.0f / (range + 1e-4f);
+        const float w = w_spatial * w_range;
+        if (w > 1e-6f) {  // SimpleWeightedECDF::add (values are finite here)
+          lo.push_back({nlo, w});
+          up.push_back({nu, w});
+        }
+        ++valid;
+      }
+      if (valid >= cfg.min_valid_neighbors) {
+        const float lower = weightedQuantile(lo, cfg.quantile_lower);
+        const float upper = weightedQuantile(up, cfg.quantile_upper);
+        if (std::isfinite(lower) && std::isfinite(upper)) {
+          upper_buffer[l] = upper;
+          lower_buffer[l] = lower;
+        }
+      }
+    }
+  }
+  upper_mat = upper_buffer;
+  lower_mat = lower_buffer;
+}
+
+// ───────────────────────────── feature extraction ("next" row) ───────────────
+// fastdem/src/feature_extraction.cpp:28-118 + nanopcl::geometry::computePCA
+// (nanopcl/geometry/impl/pca.hpp:67-90), which calls Eigen's
+// SelfAdjointEigenSolver<Matrix3f>::computeDirect.  Eigen is not in this container: the
+// closed-form 3x3 solver below restates Eigen 3.4's published algorithm (shift by trace/3,
+// scale to [-1,1], trigonometric roots, eigenvectors as row cross products) — PARITY UNPINNED
+// beyond the reference's own assertions (flat plane, tilted plane, step edge:
+// test_postprocess.cpp:273-345).  Matrices are symmetric 3x3, stored m[i][j].
+struct Eig3 {
+  float val[3];     // ascending
+  float vec[3][3];  // vec[k] = eigenvector of val[k]
+};
+inline void eig3_cross(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline float eig3_sqnorm(const float* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
+// kernel of a rank-2 symmetric matrix (Eigen's extract_kernel)
+inline void eig3_kernel(const float m[3][3], float* res, float* representative) {
+  int i0 = 0;
+  float best = std::fabs(m[0][0]);
+  for (int i = 1; i < 3; ++i)
+    if (std::fabs(m[i][i]) > best) { best = std::fabs(m[i][i]); i0 = i; }
+  float col[3][3];
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) col[j][i] = m[i][j];
+  for (int i = 0; i < 3; ++i) representative[i] = col[i0][i];
+  float c0[3], c1[3];
+  eig3_cross(representative, col[(i0 + 1) % 3], c0);
+  eig3_cross(representative, col[(i0 + 2) % 3], c1);
+  const float n0 = eig3_sqnorm(c0), n1 = eig3_sqnorm(c1);
+  if (n0 > n1) { const float s = std::sqrt(n0); for (int i = 0; i < 3; ++i) res[i] = c0[i] / s; }
+  else { const float s = std::sqrt(n1); for (int i = 0; i < 3; ++i) res[i] = c1[i] / s; }
+}
+inline Eig3 eig3_direct(const float cov[3][3]) {
+  Eig3 out;
+  const float eps = std::numeric_limits<float>::epsilon();
+  const float shift = (cov[0][0] + cov[1][1] + cov[2][2]) / 3.0f;
+  float m[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m[i][j] = (i >= j) ? cov[i][j] : cov[j][i];  // lower triangle view
+  for (int i = 0; i < 3; ++i) m[i][i] -= shift;
+  float scale = 0.0f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(m[i][j]));
+  if (scale > 0.0f)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) m[i][j] /= scale;
+  // computeRoots: x^3 - c2 x^2 + c1 x - c0 = 0
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[1][0] * m[2][0] * m[2][1] -
+                   m[0][0] * m[2][1] * m[2][1] - m[1][1] * m[2][0] * m[2][0] - m[2][2] * m[1][0] * m[1][0];
+  const float c1 = m[0][0] * m[1][1] - m[1][0] * m[1][0] + m[0][0] * m[2][2] - m[2][0] * m[2][0] +
+                   m[1][1] * m[2][2] - m[2][1] * m[2][1];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  const float inv3 = 1.0f / 3.0f, sqrt3 = std::sqrt(3.0f);
+  const float c2_3 = c2 * inv3;
+  float a_3 = (c2 * c2_3 - c1) * inv3;
+  a_3 = std::max(a_3, 0.0f);
+  const float half_b = 0.5f * (c0 + c2_3 * (2.0f * c2_3 * c2_3 - c1));
+  float q = a_3 * a_3 * a_3 - half_b * half_b;
+  q = std::max(q, 0.0f);
+  const float rho = std::sqrt(a_3);
+  const float theta = std::atan2(std::sqrt(q), half_b) * inv3;
+  const float ct = std::cos(theta), sn = std::sin(theta);
+  float ev[3] = {c2_3 - rho * (ct + sqrt3 * sn), c2_3 - rho * (ct - sqrt3 * sn), c2_3 + 2.0f * rho * ct};
+  float V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // V[k] = eigenvector k
+  if (!((ev[2] - ev[0]) <= eps)) {
+    float d0 = ev[2] - ev[1];
+    const float d1 = ev[1] - ev[0];
+    int k = 0, l = 2;
+    if (d0 > d1) { k = 2; l = 0; d0 = d1; }  // Eigen: swap(k, l); d0 = d1;
+    float tmp[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) tmp[i][j] = m[i][j];
+    for (int i = 0; i < 3; ++i) tmp[i][i] -= ev[k];
+    eig3_kernel(tmp, V[k], V[l]);
+    if (d0 <= 2.0f * eps * d1) {
+      const float dot = V[k][0] * V[l][0] + V[k][1] * V[l][1] + V[k][2] * V[l][2];
+      for (int i = 0; i < 3; ++i) V[l][i] -= dot * V[l][i];
+      const float nrm = std::sqrt(eig3_sqnorm(V[l]));
+      for (int i = 0; i < 3; ++i) V[l][i] /= nrm;
+    } else {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tmp[i][j] = m[i][j];
+      for (int i = 0; i < 3; ++i) tmp[i][i] -= ev[l];
+      float dummy[3];
+      eig3_kernel(tmp, V[l], dummy);
+    }
+    float c[3];
+    eig3_cross(V[2], V[0], c);
+    const float nrm = std::sqrt(eig3_sqnorm(c));
+    for (int i = 0; i < 3; ++i) V[1][i] = c[i] / nrm;
+  }
+  for (int k = 0; k < 3; ++k) {
+    out.val[k] = ev[k] * scale + shift;
+    for (int i = 0; i < 3; ++i) out.vec[k][i] = V[k][i];
+  }
+  return out;
+}
+
+inline void applyFeatureExtraction(ElevationMap& map, float analysis_radius = 0.3f,
+                                   int min_valid_neighbors = 4, float step_lower_percentile = 0.05f,
+                                   float step_upper_percentile = 0.95f) {
+  if (!map.exists(layer::elevation)) return;
+  for (const char* n : {layer::step, layer::slope, layer::roughness, layer::curvature, layer::normal_x,
+                        layer::normal_y, layer::normal_z})
+    if (!map.exists(n)) map.add(n, NAN);
+  const Matrix& elev = map.get(layer::elevation);
+  Matrix& step_mat = map.get(layer::step);
+  Matrix& slope_mat = map.get(layer::slope);
+  Matrix& rough_mat = map.get(layer::roughness);
+  Matrix& curv_mat = map.get(layer::curvature);
+  Matrix& nx_mat = map.get(layer::normal_x);
+  Matrix& ny_mat = map.get(layer::normal_y);
+  Matrix& nz_mat = map.get(layer::normal_z);
+  const double res = map.resolution();
+  const auto reg = circularRegion(analysis_radius, res);
+  const int R = map.rows(), C = map.cols();
+  const Index st = map.startIndex();
+  std::vector<float> z_vals;
+  for (int lc = 0; lc < C; ++lc) {
+    for (int lr = 0; lr < R; ++lr) {
+      const size_t l = map.lin(wrapIndex(lr + st.r, R), wrapIndex(lc + st.c, C));
+      const float center_z = elev[l];
+      if (!std::isfinite(center_z)) continue;
+      float sum[3] = {0, 0, 0};
+      float sq[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      z_vals.clear();
+      int count = 0;
+      for (const auto& e : reg) {
+        const int nr = lr + e.dr, nc = lc + e.dc;
+        if (nr < 0 || nr >= R || nc < 0 || nc >= C) continue;
+        const float nz = elev[map.lin(wrapIndex(nr + st.r, R), wrapIndex(nc + st.c, C))];
+        if (!std::isfinite(nz)) continue;
+        const float d[3] = {-e.dr * static_cast<float>(res), -e.dc * static_cast<float>(res), nz - center_z};
+        for (int i = 0; i < 3; ++i) sum[i] += d[i];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) sq[i][j] += d[i] * d[j];
+        z_vals.push_back(nz);
+        ++count;
+      }
+      if (count < min_valid_neighbors) continue;
+      const float inv_n = 1.0f / static_cast<float>(count);
+      float mean[3], cov[3][3];
+      for (int i = 0; i < 3; ++i) mean[i] = sum[i] * inv_n;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) cov[i][j] = sq[i][j] * inv_n - mean[i] * mean[j];
+      const float trace = cov[0][0] + cov[1][1] + cov[2][2];
+      if (trace < std::numeric_limits<float>::epsilon()) continue;  // computePCA: valid = false
+      const Eig3 pca = eig3_direct(cov);
+      if (pca.val[1] < 1e-8f) continue;
+      float normal[3] = {pca.vec[0][0], pca.vec[0][1], pca.vec[0][2]};
+      if (normal[2] < 0.0f)
+        for (float& v : normal) v = -v;
+      std::sort(z_vals.begin(), z_vals.end());
+      const int lo = static_cast<int>(step_lower_percentile * (count - 1));
+      const int hi = static_cast<int>(step_upper_percentile * (count - 1));
+      step_mat[l] = z_vals[hi] - z_vals[lo];
+      slope_mat[l] = std::acos(std::fabs(normal[2])) * 180.0f / static_cast<float>(M_PI);
+      rough_mat[l] = std::sqrt(pca.val[0]);
+      curv_mat[l] = (trace > 0.0f) ? std::fabs(pca.val[0] / trace) : 0.0f;
+      nx_mat[l] = normal[0];
+      ny_mat[l] = normal[1];
+      nz_mat[l] = normal[2];
     }
   }
 }

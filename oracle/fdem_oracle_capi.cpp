@@ -391,3 +391,33 @@ int64_t orc_from_pointcloud2(const uint8_t* data, size_t n, const orc_pc2_layout
 extern "C" void orc_spatial_smoothing(void* mp, const char* layer, int kernel_size, int min_valid) {
   applySpatialSmoothing(*static_cast<ElevationMap*>(mp), layer, kernel_size, min_valid);
 }
+
+extern "C" void orc_uncertainty_fusion(void* mp, float search_radius, float spatial_sigma,
+                                       float quantile_lower, float quantile_upper, int min_valid) {
+  UncertaintyFusionConfig c;
+  c.enabled = true;
+  c.search_radius = search_radius;
+  c.spatial_sigma = spatial_sigma;
+  c.quantile_lower = quantile_lower;
+  c.quantile_upper = quantile_upper;
+  c.min_valid_neighbors = min_valid;
+  applyUncertaintyFusion(*static_cast<ElevationMap*>(mp), c);
+}
+
+extern "C" void orc_feature_extraction(void* mp, float analysis_radius, int min_valid,
+                                       float step_lower_percentile, float step_upper_percentile) {
+  applyFeatureExtraction(*static_cast<ElevationMap*>(mp), analysis_radius, min_valid,
+                         step_lower_percentile, step_upper_percentile);
+}
+
+// Eigen-style direct 3x3 symmetric eigen-decomposition (row-major 9 floats in, 3 + 9 out)
+extern "C" void orc_eig3(const float* cov9, float* val3, float* vec9) {
+  float c[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) c[i][j] = cov9[i * 3 + j];
+  const Eig3 e = eig3_direct(c);
+  for (int k = 0; k < 3; ++k) {
+    val3[k] = e.val[k];
+    for (int i = 0; i < 3; ++i) vec9[k * 3 + i] = e.vec[k][i];
+  }
+}

@@ -310,3 +310,31 @@ def load_npz(omap, filename):
     buf = C.create_string_buffer(256)
     ok = bool(L.orc_load_npz(omap.h, str(filename).encode(), buf, 256))
     return ok, buf.value.decode()
+
+
+def uncertainty_fusion(omap, search_radius=0.15, spatial_sigma=0.05, quantile_lower=0.01,
+                       quantile_upper=0.99, min_valid=3):
+    L = lib()
+    L.orc_uncertainty_fusion.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+    L.orc_uncertainty_fusion.restype = None
+    L.orc_uncertainty_fusion(omap.h, search_radius, spatial_sigma, quantile_lower, quantile_upper, min_valid)
+
+
+def feature_extraction(omap, analysis_radius=0.3, min_valid=4, step_lower=0.05, step_upper=0.95):
+    L = lib()
+    L.orc_feature_extraction.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_float]
+    L.orc_feature_extraction.restype = None
+    L.orc_feature_extraction(omap.h, analysis_radius, min_valid, step_lower, step_upper)
+
+
+def eig3(cov):
+    """Eigen-style direct 3x3 solver of the oracle: (ascending eigenvalues, eigenvectors as rows)."""
+    L = lib()
+    L.orc_eig3.argtypes = [C.POINTER(C.c_float)] * 3
+    L.orc_eig3.restype = None
+    a = np.ascontiguousarray(cov, dtype=np.float32).reshape(9)
+    val = np.zeros(3, np.float32)
+    vec = np.zeros(9, np.float32)
+    L.orc_eig3(a.ctypes.data_as(C.POINTER(C.c_float)), val.ctypes.data_as(C.POINTER(C.c_float)),
+               vec.ctypes.data_as(C.POINTER(C.c_float)))
+    return val, vec.reshape(3, 3)

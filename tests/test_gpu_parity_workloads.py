@@ -34,3 +34,14 @@ def test_c1_basic_layer_policy(fdem):
     cfg.move_clear_policy = 1
     gmap, omap, *_ = run_pair(fdem, wl, 8, cfg)
     compare_maps(gmap, omap)
+
+
+@pytest.mark.parametrize("bucket_bits", [9, 10])
+@pytest.mark.parametrize("name,n_scans", [("c1_vlp16_local", 6), ("c3_rgbd_p2", 7)])
+def test_bucket_sizes_give_the_same_map(fdem, monkeypatch, name, n_scans, bucket_bits):
+    """The tile path's bucket size (512 or 1024 cells; K3t is compiled for both) is a
+    scheduling choice: both must reproduce the oracle."""
+    monkeypatch.setenv("FDEM_BUCKET_BITS", str(bucket_bits))
+    wl = syn.WORKLOADS[name]
+    gmap, omap, *_ = run_pair(fdem, wl, n_scans)
+    compare_maps(gmap, omap)

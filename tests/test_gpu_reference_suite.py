@@ -630,3 +630,72 @@ def test_spatial_smoothing_matches_oracle(fdem):  # test_postprocess.cpp:249-271
     fdem.applySpatialSmoothing(g, "nonexistent_layer")   # no-op like the reference
     with pytest.raises(fdem.FdemError):
         fdem.applySpatialSmoothing(g, "elevation", 4, 5)
+
+
+def _random_terrain(rng, n=40, hole=0.25):
+    r, c = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    e = (0.3 * np.sin(0.35 * r) * np.cos(0.27 * c) + 0.02 * rng.standard_normal((n, n))).astype(np.float32)
+    e[20:, 25:] += np.float32(0.8)                     # a step edge
+    e[rng.uniform(size=e.shape) < hole] = np.nan
+    return e
+
+
+def test_uncertainty_fusion_matches_oracle(fdem):  # test_postprocess.cpp:193-247
+    rng = np.random.RandomState(21)
+    g = fdem.ElevationMap(4.0, 4.0, 0.1)
+    o = ob.OracleMap(4.0, 4.0, 0.1)
+    fdem.applyUncertaintyFusion(g)                      # no bound layers: no-op, nothing added
+    assert not g.exists("upper_bound")
+    e = _random_terrain(rng)
+    spread = rng.uniform(0.01, 0.3, size=e.shape).astype(np.float32)
+    for m in (g, o):
+        m.add("upper_bound")
+        m.add("lower_bound")
+        m.set("elevation", np.asfortranarray(e))
+        m.set("upper_bound", np.asfortranarray(e + spread))
+        m.set("lower_bound", np.asfortranarray(e - spread))
+        m.move((0.7, -0.4))                             # circular buffer wraps, edge stripes are NaN
+    for kw in (dict(), dict(search_radius=0.25, spatial_sigma=0.1, quantile_lower=0.1, quantile_upper=0.8,
+                            min_valid_neighbors=5)):
+        fdem.applyUncertaintyFusion(g, **kw)
+        ob.uncertainty_fusion(o, kw.get("search_radius", 0.15), kw.get("spatial_sigma", 0.05),
+                              kw.get("quantile_lower", 0.01), kw.get("quantile_upper", 0.99),
+                              kw.get("min_valid_neighbors", 3))
+        for name in ("upper_bound", "lower_bound"):
+            # every output is one of the input samples: a quantile picks, it does not blend
+            compare_layer(name, g.get(name), o.get(name), rtol=0, atol=0)
+    fdem.applyUncertaintyFusion(g, enabled=False)       # disabled = no-op
+    with pytest.raises(fdem.FdemError):
+        fdem.applyUncertaintyFusion(g, search_radius=0.7)   # 7 cells > compiled neighbourhood
+
+
+def test_feature_extraction_matches_oracle(fdem):  # test_postprocess.cpp:273-350
+    rng = np.random.RandomState(22)
+    g = fdem.ElevationMap(4.0, 4.0, 0.1)
+    o = ob.OracleMap(4.0, 4.0, 0.1)
+    fdem.applyFeatureExtraction(g, 0.3, 4)               # all NaN: layers created, nothing computed
+    assert g.exists("slope") and not np.isfinite(g.get("slope")).any()
+    e = _random_terrain(rng, hole=0.15)
+    for m in (g, o):
+        m.set("elevation", np.asfortranarray(e))
+        m.move((-0.3, 0.6))
+    fdem.applyFeatureExtraction(g, 0.3, 4)
+    ob.feature_extraction(o, 0.3, 4)
+    n_ok = int(np.isfinite(o.get("slope")).sum())
+    assert n_ok > 500
+    compare_layer("step", g.get("step"), o.get("step"), rtol=0, atol=0)   # order statistics: exact
+    # PCA outputs go through sin/cos/atan2/acos, whose last bits differ between libm and CUDA
+    compare_layer("roughness", g.get("roughness"), o.get("roughness"), rtol=1e-3, atol=1e-5)
+    compare_layer("curvature", g.get("curvature"), o.get("curvature"), rtol=1e-3, atol=1e-6)
+    for name in ("_normal_x", "_normal_y", "_normal_z"):
+        compare_layer(name, g.get(name), o.get(name), rtol=1e-4, atol=1e-4)
+    compare_layer("slope", g.get("slope"), o.get("slope"), rtol=1e-4, atol=0.05)  # acos near 1
+    # reference known answers on the GPU path: flat plane, tilted plane
+    g2 = fdem.ElevationMap(10.0, 10.0, 0.5)
+    g2.set("elevation", np.asfortranarray(np.ones((20, 20), np.float32)))
+    fdem.applyFeatureExtraction(g2, 0.6, 4)
+    assert abs(g2.get("slope")[10, 10]) < 1.0 and abs(g2.get("_normal_z")[10, 10] - 1.0) < 0.01
+    assert abs(g2.get("roughness")[10, 10]) < 1e-3 and abs(g2.get("step")[10, 10]) < 1e-3
+    g2.set("elevation", np.asfortranarray(np.fromfunction(lambda r, c: r * 0.25, (20, 20)).astype(np.float32)))
+    fdem.applyFeatureExtraction(g2, 0.6, 4)
+    assert abs(g2.get("slope")[10, 10] - 26.565) < 0.01

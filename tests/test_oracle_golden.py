@@ -574,3 +574,91 @@ def test_spatial_smoothing_removes_spike():  # test_postprocess.cpp:249-266
     ob.spatial_smoothing(m, "elevation", 3, 5)
     assert abs(m.get("elevation")[10, 10] - 1.0) < 0.01
     ob.spatial_smoothing(m, "nonexistent_layer")  # :268-271 must not crash
+
+
+# ───────────── uncertainty fusion / feature extraction (test_postprocess.cpp:191-345) ─────────────
+def _bounds_block(m):
+    up = np.full((20, 20), NAN, np.float32)
+    lo = np.full((20, 20), NAN, np.float32)
+    el = np.full((20, 20), NAN, np.float32)
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            h = np.float32(1.0) + np.float32(0.1) * dr
+            el[10 + dr, 10 + dc] = h
+            up[10 + dr, 10 + dc] = h + np.float32(0.2)
+            lo[10 + dr, 10 + dc] = h - np.float32(0.2)
+    m.set("elevation", el)
+    m.add("upper_bound")
+    m.add("lower_bound")
+    m.set("upper_bound", up)
+    m.set("lower_bound", lo)
+    return up, lo
+
+
+def test_uncertainty_fusion_computes_bounds():  # :193-225
+    m = ob.OracleMap(10.0, 10.0, 0.5)
+    up0, lo0 = _bounds_block(m)
+    ob.uncertainty_fusion(m, 0.6, 0.3, 0.01, 0.99, 1)
+    up, lo = m.get("upper_bound"), m.get("lower_bound")
+    assert np.isfinite(up[10, 10]) and np.isfinite(lo[10, 10]) and up[10, 10] > lo[10, 10]
+    # radius 0.6 m on a 0.5 m grid reaches the four edge neighbours: quantile 0.99 of the
+    # upper bounds {1.1, 1.2, 1.2, 1.2, 1.3} is the largest, quantile 0.01 of the lower the smallest
+    assert abs(up[10, 10] - 1.3) < 1e-6
+    assert abs(lo[10, 10] - 0.7) < 1e-6
+    # cells outside the block stay NaN
+    assert np.isnan(up[5, 5]) and np.isnan(lo[5, 5])
+
+
+def test_uncertainty_fusion_skips_missing_bounds():  # :227-237
+    m = ob.OracleMap(10.0, 10.0, 0.5)
+    ob.uncertainty_fusion(m)  # no bound layers: early return, nothing added
+    assert not m.exists("upper_bound")
+
+
+def test_feature_extraction_flat_tilted_step():  # :273-345
+    m = ob.OracleMap(10.0, 10.0, 0.5)
+    m.set("elevation", np.ones((20, 20), np.float32))
+    ob.feature_extraction(m, 0.6, 4)
+    for name in ("step", "slope", "roughness", "curvature", "_normal_x", "_normal_y", "_normal_z"):
+        assert m.exists(name)
+    assert abs(m.get("slope")[10, 10]) < 1.0
+    assert abs(m.get("roughness")[10, 10]) < 1e-3
+    assert abs(m.get("step")[10, 10]) < 1e-3
+    assert abs(m.get("_normal_z")[10, 10] - 1.0) < 0.01
+    # tilted plane: z = logical row * res * 0.5 -> slope = atan(0.5) = 26.57 deg
+    e = np.fromfunction(lambda r, c: r * 0.5 * 0.5, (20, 20)).astype(np.float32)
+    m.set("elevation", e)
+    ob.feature_extraction(m, 0.6, 4)
+    s = m.get("slope")[10, 10]
+    assert 10.0 < s < 45.0 and abs(s - math.degrees(math.atan(0.5))) < 0.01
+    # step edge between the column halves
+    e = np.zeros((20, 20), np.float32)
+    e[:, 10:] = 1.0
+    m.set("elevation", e)
+    ob.feature_extraction(m, 0.6, 4)
+    assert m.get("step")[10, 10] > 0.5
+
+
+def test_feature_extraction_skips_nan_cells():  # :342-350
+    m = ob.OracleMap(10.0, 10.0, 0.5)
+    ob.feature_extraction(m, 0.6, 4)
+    assert m.exists("slope") and not np.isfinite(m.get("slope")[10, 10])
+
+
+def test_direct_eigen_solver_against_lapack():
+    """The oracle restates Eigen's closed-form 3x3 solver (Eigen itself is not available here):
+    its eigenvalues / eigenvectors must agree with LAPACK on random covariance matrices."""
+    rng = np.random.RandomState(0)
+    for t in range(500):
+        A = (rng.randn(3, 3) * rng.choice([1e-3, 1.0, 10.0])).astype(np.float32)
+        S = (A @ A.T).astype(np.float32)
+        if t % 5 == 0:
+            S[2, :] *= 1e-2
+            S[:, 2] *= 1e-2
+        val, vec = ob.eig3(S)
+        w, v = np.linalg.eigh(S.astype(np.float64))
+        assert np.abs(val - w).max() <= 5e-5 * max(np.abs(w).max(), 1e-30)
+        gaps = np.diff(w) / max(np.abs(w).max(), 1e-30)
+        if gaps.min() > 1e-2:  # well separated: eigenvectors are defined up to sign
+            for k in range(3):
+                assert abs(np.dot(vec[k], v[:, k])) > 0.999
