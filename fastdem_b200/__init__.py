@@ -9,7 +9,7 @@ from .capi import (EST_KALMAN, EST_P2QUANTILE, MODE_GLOBAL, MODE_LOCAL, MOVE_CLE
                    FdemError, FdemGeometry, FdemScanStats, default_config, load_library)
 from .api import (Config, ElevationMap, ElevationMapping, EstimationType, FastDEM, MappingMode,
                   PointCloud, PointCloud2, SensorType, applyFeatureExtraction, applyInpainting, applyRaycasting, applySpatialSmoothing,
-                  applyUncertaintyFusion, layer, voxelGridAny)
+                  applyUncertaintyFusion, layer, toPointCloud2, voxelGridAny)
 
 from . import io_npz as io  # fastdem::io::{saveNpz, loadNpz}
 from .config_yaml import loadConfig, parseConfig
@@ -18,7 +18,7 @@ __all__ = [
     "io", "loadConfig", "parseConfig",
     "Config", "ElevationMap", "ElevationMapping", "EstimationType", "FastDEM", "MappingMode",
     "PointCloud", "PointCloud2", "SensorType", "applyFeatureExtraction", "applyInpainting", "applyRaycasting",
-    "applySpatialSmoothing", "applyUncertaintyFusion", "layer", "voxelGridAny",
+    "applySpatialSmoothing", "applyUncertaintyFusion", "layer", "toPointCloud2", "voxelGridAny",
     "FdemConfig", "FdemError", "FdemGeometry", "FdemScanStats", "default_config", "load_library",
 ]
 __version__ = "0.1.0"

@@ -787,3 +787,25 @@ def applyFeatureExtraction(map: ElevationMap, analysis_radius: float = 0.3, min_
     lib = capi.load_library()
     check(lib.fdem_feature_extraction(map.handle, analysis_radius, min_valid_neighbors,
                                       step_lower_percentile, step_upper_percentile))
+
+
+def toPointCloud2(map: ElevationMap, elevation_layer: str = "elevation", sub_start=None, sub_size=None,
+                  stamp: int = 0) -> PointCloud2:
+    """fastdem::ros::toPointCloud2Impl (include/fastdem/bridge/ros/impl.hpp:29-174): the map as a
+    PointCloud2 message (packed on the device).  sub_start/sub_size = buffer start index / size of
+    a sub-region; default = the full map."""
+    lib = capi.load_library()
+    w, ps, nf = C.c_uint32(0), C.c_uint32(0), C.c_int32(0)
+    r0, c0 = sub_start if sub_start is not None else (0, 0)
+    nr, nc = sub_size if sub_size is not None else (-1, -1)
+    check(lib.fdem_map_pack_pointcloud2(map.handle, elevation_layer.encode(), r0, c0, nr, nc,
+                                        C.byref(w), C.byref(ps), C.byref(nf)))
+    fields = []
+    buf = C.create_string_buffer(128)
+    off = C.c_uint32(0)
+    for i in range(nf.value):
+        check(lib.fdem_map_pointcloud2_field(map.handle, i, buf, 128, C.byref(off)))
+        fields.append((buf.value.decode(), off.value, PF_FLOAT32))
+    data = np.zeros(max(w.value * ps.value, 1), np.uint8)
+    check(lib.fdem_map_pointcloud2_data(map.handle, data.ctypes.data, None))
+    return PointCloud2(data[:w.value * ps.value], w.value, 1, ps.value, fields, map.getFrameId(), stamp)

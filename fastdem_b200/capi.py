@@ -122,6 +122,10 @@ SIGNATURES = {
     "fdem_voxel_grid_any": (_ST, [_P, _f32p, C.c_size_t, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]),
     "fdem_inpaint": (_ST, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "fdem_spatial_smoothing": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32]),
+    "fdem_map_pack_pointcloud2": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
+    "fdem_map_pointcloud2_field": (_ST, [_P, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_uint32)]),
+    "fdem_map_pointcloud2_data": (_ST, [_P, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fdem_uncertainty_fusion": (_ST, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "fdem_feature_extraction": (_ST, [_P, C.c_float, C.c_int32, C.c_float, C.c_float]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),

@@ -101,6 +101,15 @@ struct fdem_map {
   cudaEvent_t ev_scan[kResultRing] = {};
   uint64_t seq = 0;                   // scans enqueued so far (ticket of the next scan)
   LaunchCounter lc;
+  // cell-sized scratch layers for the post-process stencils (snapshots / double buffers),
+  // allocated on first use and kept
+  float* d_tmp[2] = {nullptr, nullptr};
+  // last fdem_map_pack_pointcloud2() result (device resident)
+  float* d_pack = nullptr;
+  size_t pack_cap_bytes = 0;
+  uint32_t* d_pack_cols = nullptr;    // [2 * cols + 1] per-column counts, offsets, total
+  std::vector<std::string> pack_fields;
+  uint32_t pack_width = 0;
 };
 
 namespace {
@@ -1035,6 +1044,10 @@ fdem_status fdem_map_destroy(fdem_map* m) {
   cudaFree(m->d_touched_minz);
   cudaFree(m->d_ray_min_enc);
   cudaFree(m->d_hits);
+  cudaFree(m->d_pack);
+  cudaFree(m->d_pack_cols);
+  cudaFree(m->d_tmp[0]);
+  cudaFree(m->d_tmp[1]);
   cudaFreeHost(m->h_result);
   for (cudaEvent_t e : m->ev_scan)
     if (e) cudaEventDestroy(e);

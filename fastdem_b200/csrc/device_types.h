@@ -251,7 +251,7 @@ void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const
                             LaunchCounter& lc);
 int launch_median_filter(const float* src, float* dst, const DeviceState* st, int kernel_size,
                          int min_valid, cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
-// returns 1 when radius / resolution exceeds the compiled neighbourhood (5 cells)
+// returns 1 when radius / resolution exceeds the compiled neighbourhood (8 cells)
 int launch_uncertainty_fusion(const float* upper_in, const float* lower_in, float* upper_out,
                               float* lower_out, const DeviceState* st, float radius, double res,
                               float spatial_sigma, float q_lower, float q_upper, int min_valid,
@@ -259,6 +259,13 @@ int launch_uncertainty_fusion(const float* upper_in, const float* lower_in, floa
 int launch_feature_extraction(const float* elev, float* const out7[7], const DeviceState* st,
                               float radius, double res, int min_valid, float p_lo, float p_hi,
                               cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
+// map -> PointCloud2 body.  phase 0: per-column counts + exclusive scan (+ total); phase 1:
+// ordered write of `total` points of (3 + n_fields) floats
+void launch_pack_pointcloud2(const float* elev, const float* const* fields, int n_fields, int rows,
+                             int cols, int sub_r0, int sub_c0, int sub_rows, int sub_cols,
+                             const DeviceState* st, uint32_t* col_count, uint32_t* col_offset,
+                             uint32_t* total, float* out, int phase, cudaStream_t s,
+                             LaunchCounter& lc);
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 

@@ -436,8 +436,8 @@ median_filter_kernel(const float* __restrict__ src, float* __restrict__ dst,
 // tree (un-vendored nanoGrid), so they are restated from the call sites:
 // offsets with (float)((dr^2+dc^2) res^2) <= radius^2, centre included, dr outer / dc inner,
 // restricted to in-bounds LOGICAL cells ──
-constexpr int kMaxRegionHalf = 5;
-constexpr int kMaxRegionCells = (2 * kMaxRegionHalf + 1) * (2 * kMaxRegionHalf + 1);  // 121
+constexpr int kMaxRegionHalf = 8;
+constexpr int kMaxRegionCells = (2 * kMaxRegionHalf + 1) * (2 * kMaxRegionHalf + 1);  // 289
 
 // weighted quantile of samples already sorted by value (SimpleWeightedECDF::quantile,
 // uncertainty_fusion.cpp:62-90)
@@ -735,6 +735,105 @@ feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers ou
   out.nz[i] = normal[2];
 }
 
+// ── map -> sensor_msgs/PointCloud2 body (toPointCloud2Impl,
+// fastdem/include/fastdem/bridge/ros/impl.hpp:29-174): one point per cell with a finite
+// elevation; columns outer, rows inner, both starting at sub_start and wrapping around the
+// circular buffer.  One warp per sub-region column: count -> scan -> ordered write. ──
+struct PackParams {
+  const float* elev;
+  const float* field[kMaxLayers];  // visible float layers, then (optionally) the colour bits
+  int32_t n_fields;                // entries in field[]
+  int32_t rows, cols;              // buffer size (unsharded map)
+  int32_t sub_r0, sub_c0, sub_rows, sub_cols;
+};
+
+__global__ void __launch_bounds__(kBlock)
+pack_count_kernel(const __grid_constant__ PackParams p, uint32_t* __restrict__ col_count) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.sub_cols) return;
+  const size_t base = static_cast<size_t>((p.sub_c0 + warp) % p.cols) * p.rows;
+  uint32_t n = 0;
+  for (int i = lane; i < p.sub_rows; i += 32)
+    n += isfinite(p.elev[base + (p.sub_r0 + i) % p.rows]) ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) n += __shfl_down_sync(0xffffffffu, n, d);
+  if (lane == 0) col_count[warp] = n;
+}
+
+// exclusive scan of the per-column counts (<= a few thousand entries): one CTA
+__global__ void __launch_bounds__(1024)
+pack_scan_kernel(const uint32_t* __restrict__ col_count, uint32_t* __restrict__ col_offset, int n,
+                 uint32_t* __restrict__ total) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int j = base + threadIdx.x;
+    const uint32_t v = j < n ? col_count[j] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wprefix = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      const uint32_t x = s_warp[w];
+      if (w < warp) wprefix += x;
+      all += x;
+    }
+    if (j < n) col_offset[j] = s_running + wprefix + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_running += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_running;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pack_write_kernel(const __grid_constant__ PackParams p, const DeviceState* __restrict__ st,
+                  const uint32_t* __restrict__ col_offset, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.sub_cols) return;
+  const GridGeom g = st->geom;
+  const double origin_x = g.pos[0] + g.len[0] / 2.0 - g.res / 2.0;
+  const double origin_y = g.pos[1] + g.len[1] / 2.0 - g.res / 2.0;
+  const int bc = (p.sub_c0 + warp) % p.cols;
+  const int uc = (bc - g.start[1] + p.cols) % p.cols;
+  const float y = static_cast<float>(origin_y - uc * g.res);
+  const size_t base = static_cast<size_t>(bc) * p.rows;
+  const int step = 3 + p.n_fields;  // floats per point
+  uint32_t pos = col_offset[warp];
+  for (int i0 = 0; i0 < p.sub_rows; i0 += 32) {
+    const int i = i0 + lane;
+    float z = nanf_();
+    size_t idx = 0;
+    int br = 0;
+    if (i < p.sub_rows) {
+      br = (p.sub_r0 + i) % p.rows;
+      idx = base + br;
+      z = p.elev[idx];
+    }
+    const bool ok = isfinite(z);
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int ur = (br - g.start[0] + p.rows) % p.rows;
+      float* o = out + static_cast<size_t>(pos + __popc(m & ((1u << lane) - 1u))) * step;
+      o[0] = static_cast<float>(origin_x - ur * g.res);
+      o[1] = y;
+      o[2] = z;
+      for (int f = 0; f < p.n_fields; ++f) o[3 + f] = p.field[f][idx];
+    }
+    pos += __popc(m);
+  }
+}
+
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 8) {
   size_t b = (n + block - 1) / block;
   if (b < 1) b = 1;
@@ -834,6 +933,27 @@ int launch_feature_extraction(const float* elev, float* const out7[7], const Dev
       elev, fl, st, half, radius * radius, min_valid, p_lo, p_hi, rows_local, cols);
   ++lc.mine;
   return 0;
+}
+void launch_pack_pointcloud2(const float* elev, const float* const* fields, int n_fields, int rows,
+                             int cols, int sub_r0, int sub_c0, int sub_rows, int sub_cols,
+                             const DeviceState* st, uint32_t* col_count, uint32_t* col_offset,
+                             uint32_t* total, float* out, int phase, cudaStream_t s,
+                             LaunchCounter& lc) {
+  PackParams p{};
+  p.elev = elev;
+  for (int i = 0; i < n_fields; ++i) p.field[i] = fields[i];
+  p.n_fields = n_fields;
+  p.rows = rows; p.cols = cols;
+  p.sub_r0 = sub_r0; p.sub_c0 = sub_c0; p.sub_rows = sub_rows; p.sub_cols = sub_cols;
+  const unsigned grid = static_cast<unsigned>((static_cast<size_t>(sub_cols) * 32 + kBlock - 1) / kBlock);
+  if (phase == 0) {
+    pack_count_kernel<<<grid, kBlock, 0, s>>>(p, col_count);
+    pack_scan_kernel<<<1, 1024, 0, s>>>(col_count, col_offset, sub_cols, total);
+    lc.mine += 2;
+  } else {
+    pack_write_kernel<<<grid, kBlock, 0, s>>>(p, st, col_offset, out);
+    ++lc.mine;
+  }
 }
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {

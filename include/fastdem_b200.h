@@ -292,7 +292,7 @@ fdem_status fdem_spatial_smoothing(fdem_map* map, const char* layer_name, int32_
  * (fastdem/src/uncertainty_fusion.cpp:103-186; config/postprocess.hpp:33-40): bilateral-weighted
  * quantiles of the neighbours' lower / upper bounds, written back to upper_bound / lower_bound.
  * Missing bound layers are a no-op like in the reference (warn + return).  The neighbourhood
- * (search_radius / resolution) may span at most 5 cells: FDEM_ERR_UNSUPPORTED beyond. */
+ * (search_radius / resolution) may span at most 8 cells: FDEM_ERR_UNSUPPORTED beyond. */
 fdem_status fdem_uncertainty_fusion(fdem_map* map, float search_radius, float spatial_sigma,
                                     float quantile_lower, float quantile_upper,
                                     int32_t min_valid_neighbors);
@@ -304,6 +304,24 @@ fdem_status fdem_uncertainty_fusion(fdem_map* map, float search_radius, float sp
 fdem_status fdem_feature_extraction(fdem_map* map, float analysis_radius,
                                     int32_t min_valid_neighbors, float step_lower_percentile,
                                     float step_upper_percentile);
+
+/* fastdem::ros::toPointCloud2Impl(map, stamp, elevation_layer, sub_start, sub_size)
+ * (fastdem/include/fastdem/bridge/ros/impl.hpp:29-174): the map as a sensor_msgs/PointCloud2
+ * body, packed on the device.  One point per cell of the sub-region whose `elevation_layer`
+ * value is finite; fields (all FLOAT32, 4 bytes, in this order): x, y, z, every layer whose
+ * name does not start with '_' except the elevation layer and "color", then "rgb" (the packed
+ * colour bits) if the map has a colour layer.  Points are ordered columns outer / rows inner
+ * from (sub_row, sub_col), wrapping around the circular buffer.  sub_rows = sub_cols = -1
+ * selects the full map (start = the buffer start index), the reference's convenience overload
+ * (:170-174).  The packed body stays on the device until the next pack; read it with
+ * fdem_map_pointcloud2_data (dst: host or device, width * point_step bytes; device_ptr:
+ * optional zero-copy view) and its field names with fdem_map_pointcloud2_field. */
+fdem_status fdem_map_pack_pointcloud2(fdem_map* map, const char* elevation_layer, int32_t sub_row,
+                                      int32_t sub_col, int32_t sub_rows, int32_t sub_cols,
+                                      uint32_t* width, uint32_t* point_step, int32_t* n_fields);
+fdem_status fdem_map_pointcloud2_field(fdem_map* map, int32_t i, char* buf, int32_t cap,
+                                       uint32_t* offset);
+fdem_status fdem_map_pointcloud2_data(fdem_map* map, uint8_t* dst, const uint8_t** device_ptr);
 
 /* ── instrumentation ──────────────────────────────────────────────────────── */
 /* pipeline stages of one scan, in stream order */

@@ -1441,6 +1441,78 @@ inline void applyFeatureExtraction(ElevationMap& map, float analysis_radius = 0.
   }
 }
 
+// ───────────────────────────── map -> PointCloud2 ("next" row) ───────────────
+// toPointCloud2Impl (fastdem/include/fastdem/bridge/ros/impl.hpp:29-174): one point per cell
+// with a finite elevation, fields x, y, z, then every visible (non-'_') layer except the
+// elevation layer and color as FLOAT32, then "rgb" (the packed colour bits) when the map
+// has a colour layer; points in sub-region order, columns outer, rows inner, both starting at
+// sub_start and wrapping around the circular buffer.
+struct PackedCloud {
+  std::vector<std::string> fields;  // 4 bytes each, offset = 4 * index
+  uint32_t point_step = 0;
+  uint32_t width = 0;
+  std::vector<uint8_t> data;
+};
+inline PackedCloud toPointCloud2(const ElevationMap& map, const char* elevation_layer, Index sub_start,
+                                 int sub_rows, int sub_cols) {
+  PackedCloud msg;
+  const Matrix& elev = map.get(elevation_layer);
+  const int rows = map.rows(), cols = map.cols();
+  const Index st = map.startIndex();
+  const double res = map.resolution();
+  const double origin_x = map.position()[0] + map.length()[0] / 2.0 - res / 2.0;
+  const double origin_y = map.position()[1] + map.length()[1] / 2.0 - res / 2.0;
+  std::vector<float> row_x(sub_rows), col_y(sub_cols);
+  std::vector<int> buf_row(sub_rows), buf_col(sub_cols);
+  for (int i = 0; i < sub_rows; ++i) {
+    const int r = (sub_start.r + i) % rows;
+    buf_row[i] = r;
+    const int unwrapped = (r - st.r + rows) % rows;
+    row_x[i] = static_cast<float>(origin_x - unwrapped * res);
+  }
+  for (int j = 0; j < sub_cols; ++j) {
+    const int c = (sub_start.c + j) % cols;
+    buf_col[j] = c;
+    const int unwrapped = (c - st.c + cols) % cols;
+    col_y[j] = static_cast<float>(origin_y - unwrapped * res);
+  }
+  std::vector<std::string> float_layers;
+  bool has_color = false;
+  for (const auto& l : map.layers()) {
+    if (!l.empty() && l[0] == '_') continue;  // layer::isInternal
+    if (l == elevation_layer) continue;
+    if (l == layer::color) { has_color = true; continue; }
+    float_layers.push_back(l);
+  }
+  msg.fields = {"x", "y", "z"};
+  for (const auto& l : float_layers) msg.fields.push_back(l);
+  if (has_color) msg.fields.push_back("rgb");
+  msg.point_step = static_cast<uint32_t>(4 * msg.fields.size());
+  std::vector<const float*> ptrs;
+  for (const auto& l : float_layers) ptrs.push_back(map.get(l).data());
+  const float* color = has_color ? map.get(layer::color).data() : nullptr;
+  for (int j = 0; j < sub_cols; ++j) {
+    const size_t base = static_cast<size_t>(buf_col[j]) * rows;
+    for (int i = 0; i < sub_rows; ++i) {
+      const size_t idx = base + buf_row[i];
+      const float z = elev[idx];
+      if (!std::isfinite(z)) continue;
+      auto put = [&](float v) {
+        uint8_t b[4];
+        std::memcpy(b, &v, 4);
+        msg.data.insert(msg.data.end(), b, b + 4);
+      };
+      put(row_x[i]);
+      put(col_y[j]);
+      put(z);
+      for (const float* p : ptrs) put(p[idx]);
+      if (color) put(color[idx]);
+      ++msg.width;
+    }
+  }
+  return msg;
+}
+
 // ───────────────────────────── FastDEM pipeline ──────────────────────────────
 // fastdem/src/fastdem.cpp:122-162
 

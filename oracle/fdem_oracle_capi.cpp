@@ -421,3 +421,20 @@ extern "C" void orc_eig3(const float* cov9, float* val3, float* vec9) {
     for (int i = 0; i < 3; ++i) vec9[k * 3 + i] = e.vec[k][i];
   }
 }
+
+// map -> PointCloud2: returns the packed size; fills dst (cap bytes) and the field list
+// ('\n'-separated names) when they fit
+extern "C" int64_t orc_to_pointcloud2(void* mp, const char* elevation_layer, int sub_r0, int sub_c0,
+                                      int sub_rows, int sub_cols, uint8_t* dst, int64_t cap,
+                                      char* fields, int fields_cap, uint32_t* point_step,
+                                      uint32_t* width) {
+  const ElevationMap& m = *static_cast<ElevationMap*>(mp);
+  const PackedCloud pc = toPointCloud2(m, elevation_layer, Index{sub_r0, sub_c0}, sub_rows, sub_cols);
+  *point_step = pc.point_step;
+  *width = pc.width;
+  std::string names;
+  for (size_t i = 0; i < pc.fields.size(); ++i) names += (i ? "\n" : "") + pc.fields[i];
+  if (fields && static_cast<int>(names.size()) < fields_cap) std::strcpy(fields, names.c_str());
+  if (dst && static_cast<int64_t>(pc.data.size()) <= cap) std::memcpy(dst, pc.data.data(), pc.data.size());
+  return static_cast<int64_t>(pc.data.size());
+}

@@ -338,3 +338,22 @@ def eig3(cov):
     L.orc_eig3(a.ctypes.data_as(C.POINTER(C.c_float)), val.ctypes.data_as(C.POINTER(C.c_float)),
                vec.ctypes.data_as(C.POINTER(C.c_float)))
     return val, vec.reshape(3, 3)
+
+
+def to_pointcloud2(omap, elevation_layer="elevation", sub_start=None, sub_size=None):
+    """toPointCloud2Impl of the oracle: (fields, point_step, width, data bytes as uint8 array)."""
+    L = lib()
+    L.orc_to_pointcloud2.restype = C.c_int64
+    L.orc_to_pointcloud2.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    g = omap.geometry()
+    r0, c0 = sub_start if sub_start is not None else g["start_index"]
+    nr, nc = sub_size if sub_size is not None else (g["rows"], g["cols"])
+    ps, w = C.c_uint32(0), C.c_uint32(0)
+    names = C.create_string_buffer(4096)
+    nbytes = L.orc_to_pointcloud2(omap.h, elevation_layer.encode(), r0, c0, nr, nc, None, 0, names, 4096,
+                                  C.byref(ps), C.byref(w))
+    data = np.zeros(max(nbytes, 1), np.uint8)
+    L.orc_to_pointcloud2(omap.h, elevation_layer.encode(), r0, c0, nr, nc, data.ctypes.data, nbytes, names, 4096,
+                         C.byref(ps), C.byref(w))
+    return names.value.decode().split("\n"), ps.value, w.value, data[:nbytes]

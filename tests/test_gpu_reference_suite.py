@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
-from parity_utils import compare_layer, compare_maps
+from parity_utils import compare_layer, compare_maps, run_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -666,7 +666,7 @@ def test_uncertainty_fusion_matches_oracle(fdem):  # test_postprocess.cpp:193-24
             compare_layer(name, g.get(name), o.get(name), rtol=0, atol=0)
     fdem.applyUncertaintyFusion(g, enabled=False)       # disabled = no-op
     with pytest.raises(fdem.FdemError):
-        fdem.applyUncertaintyFusion(g, search_radius=0.7)   # 7 cells > compiled neighbourhood
+        fdem.applyUncertaintyFusion(g, search_radius=0.95)   # 10 cells > compiled neighbourhood
 
 
 def test_feature_extraction_matches_oracle(fdem):  # test_postprocess.cpp:273-350
@@ -699,3 +699,33 @@ def test_feature_extraction_matches_oracle(fdem):  # test_postprocess.cpp:273-35
     g2.set("elevation", np.asfortranarray(np.fromfunction(lambda r, c: r * 0.25, (20, 20)).astype(np.float32)))
     fdem.applyFeatureExtraction(g2, 0.6, 4)
     assert abs(g2.get("slope")[10, 10] - 26.565) < 0.01
+
+
+def _decode_pc2(fields, point_step, width, data):
+    a = np.frombuffer(bytes(data), dtype=np.uint32).reshape(width, point_step // 4) if width else np.zeros((0, point_step // 4), np.uint32)
+    return {name: a[:, k] for k, name in enumerate(fields)}
+
+
+def test_map_to_pointcloud2_matches_oracle(fdem):  # bridge/ros/impl.hpp:29-174
+    from fastdem_b200 import synthetic as syn
+    wl = syn.WORKLOADS["c3_rgbd_p2"]   # colour layer -> "rgb" field; LOCAL -> non-zero start index
+    gmap, omap, *_ = run_pair(fdem, wl, 6)
+    assert gmap.getStartIndex() != (0, 0)
+    rows, cols = gmap.getSize()
+    for sub in (None, ((rows - 7, cols - 40), (60, 150)), ((3, 5), (0, 10))):
+        kw = {} if sub is None else dict(sub_start=sub[0], sub_size=sub[1])
+        msg = fdem.toPointCloud2(gmap, "elevation", **kw)
+        of, ops, ow, od = ob.to_pointcloud2(omap, "elevation", *(sub if sub else (None, None)))
+        gf = [f[0] for f in msg.fields]
+        assert gf[:3] == ["x", "y", "z"] and gf[-1] == "rgb" and of[-1] == "rgb"
+        assert not any(n.startswith("_") for n in gf) and "elevation" not in gf and "color" not in gf
+        assert sorted(gf) == sorted(of) and msg.point_step == ops == 4 * len(gf)
+        assert msg.width == ow and msg.height == 1
+        if sub is None:
+            assert ow == int(np.isfinite(omap.get("elevation")).sum()) > 1000
+        g = _decode_pc2(gf, msg.point_step, msg.width, msg.data)
+        o = _decode_pc2(of, ops, ow, od)
+        for name in gf:   # same points, same order, same bits (NaN payloads included)
+            assert np.array_equal(g[name], o[name]), name
+    with pytest.raises(fdem.FdemError):
+        fdem.toPointCloud2(gmap, "no_such_layer")
