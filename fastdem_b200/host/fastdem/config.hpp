@@ -45,6 +45,27 @@ struct Raycasting {
   float log_odds_max = 2.0f;
   float clear_threshold = -1.0f;
 };
+// config/postprocess.hpp:25-49
+struct Inpainting {
+  bool enabled = false;
+  int max_iterations = 3;
+  int min_valid_neighbors = 2;
+};
+struct UncertaintyFusion {
+  bool enabled = false;
+  float search_radius = 0.15f;
+  float spatial_sigma = 0.05f;
+  float quantile_lower = 0.01f;
+  float quantile_upper = 0.99f;
+  int min_valid_neighbors = 3;
+};
+struct FeatureExtraction {
+  bool enabled = false;
+  float analysis_radius = 0.3f;
+  int min_valid_neighbors = 4;
+  float step_lower_percentile = 0.05f;
+  float step_upper_percentile = 0.95f;
+};
 }  // namespace config
 
 struct Config {

@@ -162,4 +162,24 @@ inline void applyInpainting(ElevationMap& map, int max_iterations = 3, int min_v
   check(fdem_inpaint(map.handle(), max_iterations, min_valid_neighbors, inplace ? 1 : 0));
 }
 
+// fastdem::applySpatialSmoothing (fastdem/include/fastdem/postprocess/spatial_smoothing.hpp:38-67)
+inline void applySpatialSmoothing(ElevationMap& map, const std::string& layer_name, int kernel_size = 3,
+                                  int min_valid_neighbors = 5) {
+  check(fdem_spatial_smoothing(map.handle(), layer_name.c_str(), kernel_size, min_valid_neighbors));
+}
+
+// fastdem::applyUncertaintyFusion (fastdem/src/uncertainty_fusion.cpp:103-186)
+inline void applyUncertaintyFusion(ElevationMap& map, const config::UncertaintyFusion& c) {
+  if (!c.enabled) return;
+  check(fdem_uncertainty_fusion(map.handle(), c.search_radius, c.spatial_sigma, c.quantile_lower,
+                                c.quantile_upper, c.min_valid_neighbors));
+}
+
+// fastdem::applyFeatureExtraction (fastdem/src/feature_extraction.cpp:28-118)
+inline void applyFeatureExtraction(ElevationMap& map, float analysis_radius = 0.3f, int min_valid_neighbors = 4,
+                                   float step_lower_percentile = 0.05f, float step_upper_percentile = 0.95f) {
+  check(fdem_feature_extraction(map.handle(), analysis_radius, min_valid_neighbors, step_lower_percentile,
+                                step_upper_percentile));
+}
+
 }  // namespace fastdem

@@ -87,6 +87,40 @@ int main() {
     EXPECT_TRUE(std::isnan(map.at(layer::elevation, ghost_idx)));
     EXPECT_NEAR(map.at(layer::ghost_removal, ghost_idx), 1.0f, 0.0f);
   }
+  {  // UncertaintyFusionComputesBounds + FeatureExtractionFlatPlane (test_postprocess.cpp:193-225, 285-297)
+    ElevationMap map(10.0f, 10.0f, 0.5f, "map");
+    map.add(layer::upper_bound, NAN);
+    map.add(layer::lower_bound, NAN);
+    const nanogrid::Index center(10, 10);
+    for (int dr = -1; dr <= 1; ++dr)
+      for (int dc = -1; dc <= 1; ++dc) {
+        const nanogrid::Index idx(center(0) + dr, center(1) + dc);
+        const float h = 1.0f + 0.1f * dr;
+        map.setAt(layer::elevation, idx, h);
+        map.setAt(layer::upper_bound, idx, h + 0.2f);
+        map.setAt(layer::lower_bound, idx, h - 0.2f);
+      }
+    config::UncertaintyFusion uf;
+    uf.enabled = true;
+    uf.search_radius = 0.6f;
+    uf.spatial_sigma = 0.3f;
+    uf.min_valid_neighbors = 1;
+    applyUncertaintyFusion(map, uf);
+    const float upper = map.at(layer::upper_bound, center), lower = map.at(layer::lower_bound, center);
+    EXPECT_TRUE(std::isfinite(upper) && std::isfinite(lower) && upper > lower);
+
+    ElevationMap flat(10.0f, 10.0f, 0.5f, "map");
+    nanogrid::Matrix ones(20, 20);
+    for (int i = 0; i < 400; ++i) ones.data()[i] = 1.0f;
+    flat.set(layer::elevation, ones);
+    applyFeatureExtraction(flat, 0.6f, 4);
+    EXPECT_TRUE(flat.exists("slope") && flat.exists("_normal_z"));
+    EXPECT_NEAR(flat.at("slope", center), 0.0f, 1.0f);
+    EXPECT_NEAR(flat.at("roughness", center), 0.0f, 0.001f);
+    EXPECT_NEAR(flat.at("_normal_z", center), 1.0f, 0.01f);
+    applySpatialSmoothing(flat, layer::elevation, 3, 5);
+    EXPECT_NEAR(flat.at(layer::elevation, center), 1.0f, 0.0f);
+  }
   {  // ElevationMap index round trip + clearAt (test_elevation_map.cpp:40-61)
     ElevationMap map(10.0f, 10.0f, 0.5f, "world");
     nanogrid::Position pos(1.0, 1.0);
