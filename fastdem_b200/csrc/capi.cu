@@ -175,6 +175,8 @@ struct fdem_mapper {
   ScanGraph sg;
   bool tile_dirty = true;  // L1 scratch must be zeroed before the next scan
   TileBuffers tb{};
+  uint32_t max_buckets = 0;   // bucket arrays are sized for the smallest bucket shape
+  bool bucket_bits_auto = true;  // pick the K3t bucket shape from the last scan's density
   // optional per-stage device timing (bench / profiling)
   bool stage_timing = false;
   std::vector<cudaEvent_t> ev_pool;               // free events
@@ -629,8 +631,8 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   pp.write_vals = tile ? 0 : 1;
   if (tile && mp->tile_dirty) {
     // first scan / after a failed scan: the L1 scratch K3t normally re-arms must be zero
-    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_count, 0, mp->tb.n_buckets * sizeof(uint32_t), s));
-    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_cursor, 0, mp->tb.n_buckets * sizeof(uint32_t), s));
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_count, 0, mp->max_buckets * sizeof(uint32_t), s));
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb.bucket_cursor, 0, mp->max_buckets * sizeof(uint32_t), s));
     mp->tile_dirty = false;
   }
 
@@ -886,6 +888,25 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
   return FDEM_OK;
 }
 
+// Bucket shape for the NEXT scans from a finished scan's statistics.  K3t runs one CTA per
+// non-empty bucket: when a scan fills only a few dozen 1024-cell buckets (a dense cloud on a
+// small patch: an RGB-D frame, a coarse map) most SMs idle while a few CTAs grind through
+// thousands of records, so the mapper switches to 256-cell buckets with one thread per cell
+// (4x the CTAs, 4x the threads per cell); when 256-cell buckets would mean thousands of jobs
+// it switches back.  The L1 scratch is all-zero between scans (K3t re-arms what it consumed)
+// and sized for the smallest shape, so switching needs no clearing; in-flight scans keep the
+// shape they were enqueued with.
+void adapt_bucket_shape(fdem_mapper* mp, uint32_t nonempty_buckets) {
+  if (!mp->bucket_bits_auto || !mp->use_tile || nonempty_buckets == 0) return;
+  uint32_t bits = mp->tb.bucket_bits;
+  if (bits == 10u && nonempty_buckets < 160u) bits = 8u;
+  else if (bits == 8u && nonempty_buckets > 800u) bits = 10u;
+  if (bits == mp->tb.bucket_bits) return;
+  mp->tb.bucket_bits = bits;
+  mp->tb.n_buckets = static_cast<uint32_t>((mp->map->cells + (1ull << bits) - 1) >> bits);
+  mp->sg.valid = false;  // K3t's function and grid change: rebuild the scan graph
+}
+
 fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
   fdem_map* m = mp->map;
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -901,6 +922,7 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
     mp->last.integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
     mp->last.voxel_box_violations = static_cast<int32_t>(r.counters[CNT_VOX_VIOLATION]);
     if (mp->last.n_cells > 0) m->obstacle_full_clear = false;
+    adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
   }
   mp->pending = false;
   if (stats) *stats = mp->last;
@@ -1331,12 +1353,19 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
     mp->use_graph = !(genv && std::string(genv) == "0");
     const char* penv = std::getenv("FDEM_PDL");
     mp->use_pdl = penv && std::string(penv) == "1";  // measured: no gain inside a graph; opt-in
-    // bucket size: 1024 cells (256-thread CTAs, 3 per SM) unless FDEM_BUCKET_BITS=9
-    // (512 cells, 128-thread CTAs, 6 per SM)
+    // K3t bucket shape (kernels_tile.cu): 1024-cell buckets to start with; after every scan
+    // whose statistics the host has seen the shape follows the scan's density (set_bucket_bits
+    // below).  FDEM_BUCKET_BITS=8|9|10 pins it.
     const char* benv = std::getenv("FDEM_BUCKET_BITS");
-    mp->tb.bucket_bits = (benv && std::string(benv) == "9") ? 9u : 10u;
-    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + (1ull << mp->tb.bucket_bits) - 1) >> mp->tb.bucket_bits);
-    const size_t nb = std::max<size_t>(mp->tb.n_buckets, 1) * sizeof(uint32_t);
+    uint32_t bits = 10u;
+    if (benv) {
+      const int v = std::atoi(benv);
+      if (v >= 8 && v <= 10) { bits = static_cast<uint32_t>(v); mp->bucket_bits_auto = false; }
+    }
+    mp->max_buckets = static_cast<uint32_t>((map->cells + 255u) >> 8);
+    mp->tb.bucket_bits = bits;
+    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + (1ull << bits) - 1) >> bits);
+    const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
     cudaError_t e2 = cudaMalloc(&mp->tb.bucket_count, nb);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_offset, nb);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_cursor, nb);
@@ -1513,6 +1542,7 @@ fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stat
     m->geom_stale = false;
   }
   if (stats->n_cells > 0) m->obstacle_full_clear = false;
+  adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
   return FDEM_OK;
 }
 

@@ -154,14 +154,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define K3T_MARK(i) do { if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[i] = clock64() - t_entry; } while (0)
 
 // ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
-// Compiled for 512-cell buckets (128 threads, ~34 KiB smem, 6 CTAs/SM) and 1024-cell
-// buckets (256 threads, ~68 KiB, 3 CTAs/SM); the mapper picks one (fdem_mapper_create).
+// Compiled for three bucket shapes; the mapper picks one per scan (capi.cu):
+//   BITS 10: 1024 cells, 256 threads (4 cells/thread), 1024-record chunks, ~68 KiB smem, 3 CTAs/SM
+//            — the default: a sparse scan (a LiDAR sweep touches ~15 % of the cells) fills
+//            few hundred buckets, one wave of CTAs
+//   BITS  9:  512 cells, 128 threads (4 cells/thread),  512-record chunks, ~34 KiB smem, 6 CTAs/SM
+//   BITS  8:  256 cells, 256 threads (1 cell/thread),  1024-record chunks, ~43 KiB smem, 3 CTAs/SM
+//            — dense scans (an RGB-D frame puts ~15 points on every touched cell of a small
+//            patch): parallelism has to come from the records, not from the map area
 template <int BITS>
 struct TileCfg {
   static constexpr int kCells = 1 << BITS;
-  static constexpr int kThr = kCells / 4;      // 4 cells per thread
+  static constexpr int kThr = BITS == 9 ? 128 : 256;
+  static constexpr int kCellsPerThread = kCells / kThr;
   static constexpr int kWarps = kThr / 32;
-  static constexpr int kChunk = kCells;        // records staged per bulk copy (32 B each)
+  static constexpr int kChunk = BITS == 9 ? 512 : 1024;  // records staged per bulk copy (32 B each)
   static constexpr int kMinBlocks = BITS == 9 ? 6 : 3;
 };
 
@@ -284,10 +291,15 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       for (uint32_t e = tid; e < cn; e += kThr) atomicAdd(&S.binoff[S.stage[e].lkey], 1u);
       __syncthreads();
       {
-        // exclusive scan of the bins: 4 consecutive bins per thread
-        const uint32_t v0 = S.binoff[tid * 4 + 0], v1 = S.binoff[tid * 4 + 1];
-        const uint32_t v2 = S.binoff[tid * 4 + 2], v3 = S.binoff[tid * 4 + 3];
-        const uint32_t t = v0 + v1 + v2 + v3;
+        // exclusive scan of the bins: kCellsPerThread consecutive bins per thread
+        constexpr int CPT = C::kCellsPerThread;
+        uint32_t v[CPT];
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          v[k] = S.binoff[tid * CPT + k];
+          t += v[k];
+        }
         uint32_t inc = t;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -300,11 +312,12 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
 #pragma unroll
         for (int w = 0; w < kWarps; ++w)
           if (w < warp) wprefix += S.warp_sums[w];
-        const uint32_t base = wprefix + inc - t;
-        S.binoff[tid * 4 + 0] = base;
-        S.binoff[tid * 4 + 1] = base + v0;
-        S.binoff[tid * 4 + 2] = base + v0 + v1;
-        S.binoff[tid * 4 + 3] = base + v0 + v1 + v2;
+        uint32_t base = wprefix + inc - t;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          S.binoff[tid * CPT + k] = base;
+          base += v[k];
+        }
       }
       __syncthreads();
       for (uint32_t e = tid; e < cn; e += kThr) {
@@ -316,8 +329,8 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
 
       // ── per-cell reduction of the sorted chunk ──
       // After the counting sort the records of cell c occupy sorted positions
-      // [binoff[c-1], binoff[c]).  Thread t owns cells t, t+kThr, t+2kThr, t+3kThr of the
-      // bucket and folds each cell's few records (pre-reduced runs, typically 0-3).  Cells
+      // [binoff[c-1], binoff[c]).  Thread t owns cells t, t+kThr, ... of the bucket and folds
+      // each cell's few records (pre-reduced runs, typically 0-3).  Cells
       // with many records in this chunk are deferred to the warp-cooperative path below.
 #pragma unroll
       for (int r = 0; r < kCells / kThr; ++r) {
@@ -487,9 +500,12 @@ int tile_estimate_debug_clocks(long long* out16) {
 }
 
 int tile_estimate_configure() {
-  cudaError_t e = cudaFuncSetAttribute(tile_estimate_kernel<9>,
+  cudaError_t e = cudaFuncSetAttribute(tile_estimate_kernel<8>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(sizeof(TileSmem<9>)));
+                                       static_cast<int>(sizeof(TileSmem<8>)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(tile_estimate_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(sizeof(TileSmem<9>)));
   if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel<10>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -506,7 +522,10 @@ void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32
                           DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
                           LaunchCounter& lc) {
   // CTAs stride over the non-empty-bucket list; one wave of co-resident CTAs at most
-  if (tb.bucket_bits == 9) {
+  if (tb.bucket_bits == 8) {
+    tile_estimate_kernel<8><<<tile_grid<8>(tb.n_buckets), TileCfg<8>::kThr, sizeof(TileSmem<8>), s>>>(
+        p, tb, counters, st_out, pub);
+  } else if (tb.bucket_bits == 9) {
     tile_estimate_kernel<9><<<tile_grid<9>(tb.n_buckets), TileCfg<9>::kThr, sizeof(TileSmem<9>), s>>>(
         p, tb, counters, st_out, pub);
   } else {
@@ -524,6 +543,9 @@ KernelDesc desc_scatter_records(uint32_t n) {
                     dim3((n + kThreads - 1) / kThreads), dim3(kThreads), 0};
 }
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits) {
+  if (bucket_bits == 8)
+    return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel<8>),
+                      dim3(tile_grid<8>(n_buckets)), dim3(TileCfg<8>::kThr), sizeof(TileSmem<8>)};
   if (bucket_bits == 9)
     return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_kernel<9>),
                       dim3(tile_grid<9>(n_buckets)), dim3(TileCfg<9>::kThr), sizeof(TileSmem<9>)};

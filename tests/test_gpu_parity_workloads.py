@@ -36,11 +36,13 @@ def test_c1_basic_layer_policy(fdem):
     compare_maps(gmap, omap)
 
 
-@pytest.mark.parametrize("bucket_bits", [9, 10])
-@pytest.mark.parametrize("name,n_scans", [("c1_vlp16_local", 6), ("c3_rgbd_p2", 7)])
+@pytest.mark.parametrize("bucket_bits", [8, 9, 10])
+@pytest.mark.parametrize("name,n_scans", [("c1_vlp16_local", 6), ("c2_lidar64_local", 4), ("c3_rgbd_p2", 7)])
 def test_bucket_sizes_give_the_same_map(fdem, monkeypatch, name, n_scans, bucket_bits):
-    """The tile path's bucket size (512 or 1024 cells; K3t is compiled for both) is a
-    scheduling choice: both must reproduce the oracle."""
+    """The tile path's bucket shape (256 / 512 / 1024 cells; K3t is compiled for all three and
+    by default follows the scan density) is a scheduling choice: every shape must reproduce
+    the oracle.  (The default-shape runs above cover the switch itself: c1 and c3 go dense
+    after their first scan.)"""
     monkeypatch.setenv("FDEM_BUCKET_BITS", str(bucket_bits))
     wl = syn.WORKLOADS[name]
     gmap, omap, *_ = run_pair(fdem, wl, n_scans)
