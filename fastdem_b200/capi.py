@@ -65,7 +65,7 @@ class FdemGeometry(C.Structure):
 
 _P = C.c_void_p
 _ST = C.c_int32
-_f32p, _u8p, _f64p = C.c_void_p, C.c_void_p, C.POINTER(C.c_double)
+_f32p, _u8p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p  # addresses are passed as plain ints
 
 # name -> (restype, argtypes); every symbol include/fastdem_b200.h declares
 SIGNATURES = {

@@ -100,6 +100,7 @@ struct fdem_map {
   uint32_t* d_result_host = nullptr;  // device-side alias of h_result[0]
   cudaEvent_t ev_scan[kResultRing] = {};
   uint64_t seq = 0;                   // scans enqueued so far (ticket of the next scan)
+  uint64_t layer_epoch = 0;           // bumped whenever a layer is added (lookup caches)
   LaunchCounter lc;
   // cell-sized scratch layers for the post-process stencils (snapshots / double buffers),
   // allocated on first use and kept
@@ -177,6 +178,10 @@ struct fdem_mapper {
   TileBuffers tb{};
   uint32_t max_buckets = 0;   // bucket arrays are sized for the smallest bucket shape
   bool bucket_bits_auto = true;  // pick the K3t bucket shape from the last scan's density
+  // by-name layer lookups of one scan (~25 string searches), cached until a layer is added
+  uint64_t cached_epoch = ~0ull;
+  EstLayers cached_L{};
+  LayerTable cached_lt{};
   // optional per-stage device timing (bench / profiling)
   bool stage_timing = false;
   std::vector<cudaEvent_t> ev_pool;               // free events
@@ -230,6 +235,7 @@ fdem_status add_layer(fdem_map* m, const char* name, float fill) {
     nl.name = name;
     FDEM_CUDA_TRY(cudaMalloc(&nl.d, std::max<size_t>(m->cells, 1) * sizeof(float)));
     m->layers.push_back(nl);
+    ++m->layer_epoch;
     l = &m->layers.back();
   }
   launch_fill(l->d, m->cells, fill, m->stream, m->lc);
@@ -661,7 +667,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   L.cp.local_mode = pp.local_mode;
   L.cp.clear_policy = cfg.move_clear_policy;
   L.cp.invalid_key = pp.invalid_key;
-  L.cp.obstacle = layer_ptr(m, "obstacle");
+  L.cp.obstacle = nullptr;  // set below from the cached layer lookup
   L.cp.touched_keys = m->d_touched_keys;
   L.cp.tile_path = tile ? 1 : 0;
   L.cp.tb = mp->tb;
@@ -700,8 +706,15 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
     ep.p2_marker = std::min(std::max(cfg.p2_elevation_marker, 0), 4);
     ep.p2_max_sample_count = std::max(cfg.p2_max_sample_count, 0.0f);
   }
-  ep.L = est_layers(m);
-  L.lt = layer_table(m);
+  if (mp->cached_epoch != m->layer_epoch) {
+    mp->cached_L = est_layers(m);
+    mp->cached_lt = layer_table(m);
+    mp->cached_epoch = m->layer_epoch;
+  }
+  ep.L = mp->cached_L;
+  L.lt = mp->cached_lt;
+  L.cp.obstacle = ep.L.obstacle;
+  L.sp.obstacle = ep.L.obstacle;
   L.tb = mp->tb;
   L.st_cur = m->d_state;
   L.st_next = m->d_state + 1;
