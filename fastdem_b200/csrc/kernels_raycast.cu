@@ -438,6 +438,7 @@ median_filter_kernel(const float* __restrict__ src, float* __restrict__ dst,
 // restricted to in-bounds LOGICAL cells ──
 constexpr int kMaxRegionHalf = 8;
 constexpr int kMaxRegionCells = (2 * kMaxRegionHalf + 1) * (2 * kMaxRegionHalf + 1);  // 289
+constexpr int kSelectMax = 16;
 
 // weighted quantile of samples already sorted by value (SimpleWeightedECDF::quantile,
 // uncertainty_fusion.cpp:62-90)
@@ -661,7 +662,8 @@ struct FeatureLayers {
 __global__ void __launch_bounds__(128)
 feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers out,
                           const DeviceState* __restrict__ st, int half, float radius_sq,
-                          int min_valid, float p_lo, float p_hi, int rows_local, int cols) {
+                          int min_valid, float p_lo, float p_hi, int rows_local, int cols,
+                          int keep_small, int keep_large) {
   const GridGeom g = st->geom;
   const size_t n = static_cast<size_t>(rows_local) * cols;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -676,7 +678,14 @@ feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers ou
   const double res2 = g.res * g.res;
   float sum[3] = {0.0f, 0.0f, 0.0f};
   float sq[3][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+  // The step feature needs two order statistics of the patch's heights.  When both ranks are
+  // near the ends (the default 5 % / 95 %), only the keep_small smallest and keep_large largest
+  // values are tracked (the host sizes them from the region's cell count); otherwise the whole
+  // patch is kept sorted.
+  const bool select = keep_small > 0;
   float z_vals[kMaxRegionCells];
+  float z_small[kSelectMax], z_large[kSelectMax];
+  int n_small = 0, n_large = 0;
   int count = 0;
   for (int dr = -half; dr <= half; ++dr) {
     for (int dc = -half; dc <= half; ++dc) {
@@ -695,13 +704,32 @@ feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers ou
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) sq[a][b] += d[a] * d[b];
-      // keep z_vals sorted (the reference sorts afterwards; same multiset)
-      int j = count;
-      while (j > 0 && nz < z_vals[j - 1]) {
-        z_vals[j] = z_vals[j - 1];
-        --j;
+      if (select) {
+        if (n_small < keep_small || nz < z_small[n_small - 1]) {  // ascending, smallest first
+          int j = n_small < keep_small ? n_small++ : n_small - 1;
+          while (j > 0 && nz < z_small[j - 1]) {
+            z_small[j] = z_small[j - 1];
+            --j;
+          }
+          z_small[j] = nz;
+        }
+        if (n_large < keep_large || nz > z_large[n_large - 1]) {  // descending, largest first
+          int j = n_large < keep_large ? n_large++ : n_large - 1;
+          while (j > 0 && nz > z_large[j - 1]) {
+            z_large[j] = z_large[j - 1];
+            --j;
+          }
+          z_large[j] = nz;
+        }
+      } else {
+        // keep z_vals sorted (the reference sorts afterwards; same multiset)
+        int j = count;
+        while (j > 0 && nz < z_vals[j - 1]) {
+          z_vals[j] = z_vals[j - 1];
+          --j;
+        }
+        z_vals[j] = nz;
       }
-      z_vals[j] = nz;
       ++count;
     }
   }
@@ -726,7 +754,8 @@ feature_extraction_kernel(const float* __restrict__ elev, const FeatureLayers ou
   }
   const int lo = static_cast<int>(p_lo * (count - 1));
   const int hi = static_cast<int>(p_hi * (count - 1));
-  out.step[i] = z_vals[hi] - z_vals[lo];
+  // ranks from the top: (count-1) - hi never exceeds the host's bound for the full region
+  out.step[i] = select ? z_large[(count - 1) - hi] - z_small[lo] : z_vals[hi] - z_vals[lo];
   out.slope[i] = acosf(fabsf(normal[2])) * 180.0f / 3.14159265358979323846f;
   out.roughness[i] = sqrtf(pca.val[0]);
   out.curvature[i] = (trace > 0.0f) ? fabsf(pca.val[0] / trace) : 0.0f;
@@ -929,8 +958,22 @@ int launch_feature_extraction(const float* elev, float* const out7[7], const Dev
   const size_t n = static_cast<size_t>(rows_local) * cols;
   if (n == 0) return 0;
   FeatureLayers fl{out7[0], out7[1], out7[2], out7[3], out7[4], out7[5], out7[6]};
+  // how many of the smallest / largest heights the two percentile ranks can ever reach:
+  // lo = int(p_lo (count-1)) and (count-1) - int(p_hi (count-1)) are non-decreasing in count,
+  // which the region's cell count bounds (+1 for float rounding)
+  int region = 0;
+  const float r2 = radius * radius;
+  for (int dr = -half; dr <= half; ++dr)
+    for (int dc = -half; dc <= half; ++dc)
+      if (static_cast<float>(static_cast<double>(dr * dr + dc * dc) * res * res) <= r2) ++region;
+  int keep_small = 0, keep_large = 0;
+  if (region > 0) {
+    const int ks = static_cast<int>(p_lo * (region - 1)) + 2;
+    const int kl = (region - 1) - static_cast<int>(p_hi * (region - 1)) + 2;
+    if (ks <= kSelectMax && kl <= kSelectMax) { keep_small = ks; keep_large = kl; }
+  }
   feature_extraction_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(
-      elev, fl, st, half, radius * radius, min_valid, p_lo, p_hi, rows_local, cols);
+      elev, fl, st, half, r2, min_valid, p_lo, p_hi, rows_local, cols, keep_small, keep_large);
   ++lc.mine;
   return 0;
 }

@@ -690,6 +690,10 @@ def test_feature_extraction_matches_oracle(fdem):  # test_postprocess.cpp:273-35
     for name in ("_normal_x", "_normal_y", "_normal_z"):
         compare_layer(name, g.get(name), o.get(name), rtol=1e-4, atol=1e-4)
     compare_layer("slope", g.get("slope"), o.get("slope"), rtol=1e-4, atol=0.05)  # acos near 1
+    # percentiles away from the ends take the kernel's keep-everything-sorted path
+    fdem.applyFeatureExtraction(g, 0.3, 4, 0.25, 0.75)
+    ob.feature_extraction(o, 0.3, 4, 0.25, 0.75)
+    compare_layer("step", g.get("step"), o.get("step"), rtol=0, atol=0)
     # reference known answers on the GPU path: flat plane, tilted plane
     g2 = fdem.ElevationMap(10.0, 10.0, 0.5)
     g2.set("elevation", np.asfortranarray(np.ones((20, 20), np.float32)))
