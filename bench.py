@@ -127,6 +127,17 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+# pipeline stage (fdem_mapper_stage_times) -> the kernels it runs
+STAGE_KERNELS = {
+    "preprocess_bin": "preprocess_bin_kernel (K1)",
+    "commit_move_clear": "commit_move_clear_kernel (K2)",
+    "sort_by_cell": "scatter_records_kernel (L1 of the 2-level sort)",
+    "segreduce_estimate": "tile_estimate_kernel<8|9|10> (K3t: per-bucket sort + segmented reduce + estimator)",
+    "voxel_raycast": "voxel_keys32 + cub radix sort + voxel_select + ray_keys + cub radix sort + "
+                     "raycast_scan + raycast_resolve (not HBM bound: per-ray DDA, L1/L2 resident)",
+}
+
+
 def algorithmic_bytes(wl, n_points, stats_list, has_i, has_c, p2):
     """B = N*b_pt + C*b_cell + C_prev*4, split per pipeline stage.
     Compulsory traffic only — no sort scratch, no intermediate copies."""
@@ -140,7 +151,17 @@ def algorithmic_bytes(wl, n_points, stats_list, has_i, has_c, p2):
         "sort_by_cell": 0.0,                                     # pure scratch traffic
         "segreduce_estimate": C * b_cell + Nv * (b_pt - 16.0),   # cell state + per-point channels
     }
-    return per_stage, n_points * b_pt + C * b_cell + C * 4.0
+    total = n_points * b_pt + C * b_cell + C * 4.0
+    V = statistics.mean(s.n_voxels for s in stats_list) if stats_list else 0.0
+    if V > 0:
+        # raycasting (not HBM bound — an L1/L2-resident per-ray DDA; the figure is its compulsory
+        # traffic only): kept points read for the voxel keys, one point per traced ray, and the
+        # per-scan clear of the `raycasting` layer + read of elevation + write of the ray minimum
+        # over the whole map (raycasting.cpp:242, 188-214)
+        M = int(round(wl.map_width / wl.resolution)) * int(round(wl.map_height / wl.resolution))
+        per_stage["voxel_raycast"] = Nv * 16.0 + V * 16.0 + M * 12.0
+        total += per_stage["voxel_raycast"]
+    return per_stage, total
 
 
 def run_reference(args, wl, rank, world):
@@ -573,7 +594,7 @@ def main():
         except Exception:
             pass
         roofline = {
-            "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": dominant, "kernel_names": STAGE_KERNELS.get(dominant), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": dom_bytes,
             "kernel_ms": dom_ms,

@@ -8,6 +8,7 @@
 // buffer — scratch, never estimator state.  Compiled with -fmad=false; the DDA follows the
 // reference's float32 arithmetic expression by expression.
 #include <float.h>
+#include <cstdlib>
 #include <math.h>
 
 #include "device_types.h"
@@ -183,95 +184,109 @@ ray_keys_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __re
 
 constexpr int kRayBatch = 8;
 
-// traceRay (raycasting.cpp:46-139): one thread per traced ray, rays sorted by length so that
-// a warp's 32 rays finish together (in input order two thirds of the lanes idle: untraced
-// entries, and short rays waiting for the longest one).
-// Measured alternatives (B200, config 4, 1.05 M points; this kernel: 260 us):
-//   input order, one cell per round trip                       540 us
+// traceRay (raycasting.cpp:46-139): one thread per traced ray.
+//  * Rays are sorted by length so that a warp's 32 rays finish together (in input order two
+//    thirds of the lanes idle: untraced entries, and short rays waiting for the longest one).
+//  * NEAR FIELD in shared memory.  Every ray starts in the sensor's cell and most rays are
+//    short (steep beams), so most cell visits fall inside a small window around the sensor.
+//    Persistent CTAs (5 per SM) each keep a 96 x 96-cell window's minima in shared memory
+//    (36 KiB), run their rays' first steps against it (a shared-memory load + a rare shared
+//    atomic instead of an uncoalesced global load + L2 atomic), and flush the window once at
+//    the end.  (64 / 96 / 128-cell windows measured: 238 / 233 / 248 us on config 4.)
+//  * FAR FIELD batched.  Outside the window the DDA runs kRayBatch cells at a time: the cell
+//    sequence does not depend on memory, so the batch's cells and exit heights are computed
+//    first, ALL their loads issued back to back, then the compares / atomics.
+// Measured alternatives (B200, config 4, 1.05 M points):
+//   input order, one cell per round trip                                     540 us
+//   length order + batched loads, no near-field window                        260 us
+//   + near-field window (this kernel)                                          233 us
 //   (azimuth sector, length) order: loads coalesce (2 sectors per request instead of ~30)
 //     but lanes in lockstep on the same cells all see the same stale minimum and all
-//     fire: 24 M atomics instead of 6 M                          355 us
-//   the same + per-CTA shared-memory hash table of the wedge's minima, one flush per
-//     cell: same-address shared atomics and probe chains          1280 us
+//     fire: 24 M atomics instead of 6 M                                        355 us
+//   the same + per-CTA shared-memory hash table of the wedge's minima          1280 us
+template <int kNear>  // near-field window: kNear x kNear cells around the sensor
 __global__ void __launch_bounds__(kBlock)
 raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
                     const float4* __restrict__ pts, const uint32_t* __restrict__ rkeys,
                     const uint32_t* __restrict__ rvals, uint32_t n_max) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_max) return;
-  if (rkeys[i] == kRayInvalid) return;  // sorted last: whole warps leave here
+  extern __shared__ uint32_t near_min[];  // [kNear * kNear], column-major in LOGICAL cells
+  constexpr int kNearHalf = kNear / 2;
   const GridGeom g = st->geom;
-  const float4 pt = __ldg(&pts[rvals[i]]);
   const int nrows = g.rows, ncols = g.cols;
+  // float32 grid math, expression by expression as the reference
   const float resolution = static_cast<float>(g.res);
   const float sx = p.origin[0], sy = p.origin[1], sz = p.origin[2];
-  const float dx = pt.x - sx;
-  const float dy = pt.y - sy;
-  const float dz = pt.z - sz;
   const float origin_x = static_cast<float>(g.pos[0]) + nrows * resolution * 0.5f;
   const float origin_y = static_cast<float>(g.pos[1]) + ncols * resolution * 0.5f;
   const float gr0 = (origin_x - sx) / resolution;
   const float gc0 = (origin_y - sy) / resolution;
-  const float gr1 = (origin_x - pt.x) / resolution;
-  const float gc1 = (origin_y - pt.y) / resolution;
-  const float dr = gr1 - gr0;
-  const float dc = gc1 - gc0;
-  int r = static_cast<int>(floorf(gr0));
-  int c = static_cast<int>(floorf(gc0));
-  int step_r, step_c;
-  float t_max_r, t_max_c, t_delta_r, t_delta_c;
-  if (fabsf(dr) > 1e-8f) {
-    step_r = (dr > 0) ? 1 : -1;
-    const float boundary = (step_r > 0) ? (r + 1.0f) : static_cast<float>(r);
-    t_max_r = (boundary - gr0) / dr;
-    t_delta_r = static_cast<float>(step_r) / dr;
-  } else {
-    step_r = 0;
-    t_max_r = 1e30f;
-    t_delta_r = 1e30f;
-  }
-  if (fabsf(dc) > 1e-8f) {
-    step_c = (dc > 0) ? 1 : -1;
-    const float boundary = (step_c > 0) ? (c + 1.0f) : static_cast<float>(c);
-    t_max_c = (boundary - gc0) / dc;
-    t_delta_c = static_cast<float>(step_c) / dc;
-  } else {
-    step_c = 0;
-    t_max_c = 1e30f;
-    t_delta_c = 1e30f;
-  }
-  const int max_steps = nrows + ncols;
+  const int r_s = static_cast<int>(floorf(gr0));  // the sensor's cell: every ray starts here
+  const int c_s = static_cast<int>(floorf(gc0));
+  const int win_r0 = r_s - kNearHalf, win_c0 = c_s - kNearHalf;
   const int start_r = g.start[0], start_c = g.start[1];
-  // The DDA is run kRayBatch cells at a time: first the batch's cells and exit heights
-  // (pure arithmetic), then ALL their loads back to back, then the compares / atomics.  The
-  // loads are independent, so one memory round trip is paid per batch instead of per cell.
-  bool was_inside = false;
-  bool done = false;
-  int s = 0;
-  while (!done) {
-    uint32_t* sl[kRayBatch];
-    uint32_t ev[kRayBatch];
-    uint32_t cv[kRayBatch];
-#pragma unroll
-    for (int k = 0; k < kRayBatch; ++k) {
-      sl[k] = nullptr;
-      ev[k] = 0u;
-      if (done) continue;
-      if (s >= max_steps) { done = true; continue; }
+  const int max_steps = nrows + ncols;
+
+  for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) near_min[h] = kEncInit;
+  __syncthreads();
+
+  for (uint32_t base = blockIdx.x * kBlock; base < n_max; base += gridDim.x * kBlock) {
+    if (rkeys[base] == kRayInvalid) break;  // sorted, untraced entries last: nothing left
+    const uint32_t i = base + threadIdx.x;
+    if (i >= n_max || rkeys[i] == kRayInvalid) continue;
+    const float4 pt = __ldg(&pts[rvals[i]]);
+    const float dz = pt.z - sz;
+    const float gr1 = (origin_x - pt.x) / resolution;
+    const float gc1 = (origin_y - pt.y) / resolution;
+    const float dr = gr1 - gr0;
+    const float dc = gc1 - gc0;
+    int r = r_s;
+    int c = c_s;
+    int step_r, step_c;
+    float t_max_r, t_max_c, t_delta_r, t_delta_c;
+    if (fabsf(dr) > 1e-8f) {
+      step_r = (dr > 0) ? 1 : -1;
+      const float boundary = (step_r > 0) ? (r + 1.0f) : static_cast<float>(r);
+      t_max_r = (boundary - gr0) / dr;
+      t_delta_r = static_cast<float>(step_r) / dr;
+    } else {
+      step_r = 0;
+      t_max_r = 1e30f;
+      t_delta_r = 1e30f;
+    }
+    if (fabsf(dc) > 1e-8f) {
+      step_c = (dc > 0) ? 1 : -1;
+      const float boundary = (step_c > 0) ? (c + 1.0f) : static_cast<float>(c);
+      t_max_c = (boundary - gc0) / dc;
+      t_delta_c = static_cast<float>(step_c) / dc;
+    } else {
+      step_c = 0;
+      t_max_c = 1e30f;
+      t_delta_c = 1e30f;
+    }
+    // The sensor cell is inside the map (precondition) and the map is convex, so once a ray
+    // has left the map it never comes back: the reference keeps stepping (its cells fail the
+    // bounds test and are ignored); stopping there changes nothing but the work.
+    bool was_inside = false;
+    bool done = false;
+    int s = 0;
+
+    // ── near field: shared-memory window ──
+    while (!done && s < max_steps) {
+      const int wr = r - win_r0, wc = c - win_c0;
+      if (static_cast<unsigned>(wr) >= static_cast<unsigned>(kNear) ||
+          static_cast<unsigned>(wc) >= static_cast<unsigned>(kNear))
+        break;  // left the window: continue in the far field
       if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
         was_inside = true;
-        int mr = r + start_r;  // == (r + start) % size: both terms are in [0, size)
-        if (mr >= nrows) mr -= nrows;
-        int mc = c + start_c;
-        if (mc >= ncols) mc -= ncols;
-        sl[k] = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
         const float t_exit = fminf(t_max_r, t_max_c);
-        ev[k] = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
+        const uint32_t e = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
+        uint32_t* slot = &near_min[wc * kNear + wr];
+        // a minimum only decreases: a value read without the atomic can only be too LARGE,
+        // so the atomic may be issued needlessly but is never skipped wrongly
+        if (e < *slot) atomicMin(slot, e);
       } else if (was_inside) {
-        // the map is convex and the sensor cell is inside: once out, the ray never comes
-        // back (the reference keeps stepping over cells that fail its bounds test)
         done = true;
-        continue;
+        break;
       }
       if (t_max_r < t_max_c) {
         if (t_max_r >= 1.0f) done = true;
@@ -282,14 +297,61 @@ raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* 
       }
       ++s;
     }
-    // Plain (L1-cacheable) loads: a minimum only ever decreases, so a stale value can only
-    // be LARGER than the true one — the atomic is then issued needlessly, never skipped
-    // wrongly.
+
+    // ── far field: global scratch, kRayBatch cells per memory round trip ──
+    while (!done) {
+      uint32_t* sl[kRayBatch];
+      uint32_t ev[kRayBatch];
+      uint32_t cv[kRayBatch];
 #pragma unroll
-    for (int k = 0; k < kRayBatch; ++k) cv[k] = sl[k] ? *sl[k] : 0u;
+      for (int k = 0; k < kRayBatch; ++k) {
+        sl[k] = nullptr;
+        ev[k] = 0u;
+        if (done) continue;
+        if (s >= max_steps) { done = true; continue; }
+        if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
+          was_inside = true;
+          int mr = r + start_r;  // == (r + start) % size: both terms are in [0, size)
+          if (mr >= nrows) mr -= nrows;
+          int mc = c + start_c;
+          if (mc >= ncols) mc -= ncols;
+          sl[k] = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
+          const float t_exit = fminf(t_max_r, t_max_c);
+          ev[k] = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
+        } else if (was_inside) {
+          done = true;
+          continue;
+        }
+        if (t_max_r < t_max_c) {
+          if (t_max_r >= 1.0f) done = true;
+          else { r += step_r; t_max_r += t_delta_r; }
+        } else {
+          if (t_max_c >= 1.0f) done = true;
+          else { c += step_c; t_max_c += t_delta_c; }
+        }
+        ++s;
+      }
+      // plain (L1-cacheable) loads: staleness is safe for the same reason as above
 #pragma unroll
-    for (int k = 0; k < kRayBatch; ++k)
-      if (sl[k] && ev[k] < cv[k]) atomicMin(sl[k], ev[k]);
+      for (int k = 0; k < kRayBatch; ++k) cv[k] = sl[k] ? *sl[k] : 0u;
+#pragma unroll
+      for (int k = 0; k < kRayBatch; ++k)
+        if (sl[k] && ev[k] < cv[k]) atomicMin(sl[k], ev[k]);
+    }
+  }
+
+  // ── flush the window: every near-field cell this CTA lowered, once ──
+  __syncthreads();
+  for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) {
+    const uint32_t v = near_min[h];
+    if (v == kEncInit) continue;
+    const int r = win_r0 + (h % kNear), c = win_c0 + (h / kNear);  // in the map: only such cells are written
+    int mr = r + start_r;
+    if (mr >= nrows) mr -= nrows;
+    int mc = c + start_c;
+    if (mc >= ncols) mc -= ncols;
+    uint32_t* slot = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
+    if (v < __ldcg(slot)) atomicMin(slot, v);
   }
 }
 
@@ -914,7 +976,24 @@ void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const fl
                          const uint32_t* rkeys, const uint32_t* rvals, uint32_t n_max,
                          cudaStream_t s, LaunchCounter& lc) {
   if (n_max == 0) return;
-  raycast_scan_kernel<<<(n_max + kBlock - 1) / kBlock, kBlock, 0, s>>>(p, st, pts, rkeys, rvals, n_max);
+  // near-field window size / persistent CTAs per SM (FDEM_RAY_NEAR=64|96|128 overrides)
+  static int near = -1;
+  if (near < 0) {
+    const char* e = std::getenv("FDEM_RAY_NEAR");
+    near = e ? std::atoi(e) : 96;
+    if (near != 64 && near != 96 && near != 128) near = 96;
+  }
+  const uint32_t chunks = (n_max + kBlock - 1) / kBlock;
+  auto launch = [&](auto kernel, int kn, uint32_t ctas_per_sm) {
+    const size_t smem = sizeof(uint32_t) * kn * kn;
+    // opt-in to > 48 KiB of dynamic shared memory (per device, so not cached in a static)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const uint32_t grid = chunks < 148u * ctas_per_sm ? chunks : 148u * ctas_per_sm;
+    kernel<<<grid, kBlock, smem, s>>>(p, st, pts, rkeys, rvals, n_max);
+  };
+  if (near == 64) launch(raycast_scan_kernel<64>, 64, 8u);
+  else if (near == 96) launch(raycast_scan_kernel<96>, 96, 5u);
+  else launch(raycast_scan_kernel<128>, 128, 3u);
   ++lc.mine;
 }
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* /*st*/,
