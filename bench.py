@@ -294,6 +294,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_lidar64_local")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="c5_global at N>1: how the stripes get the scan — 'peer': every rank's K1 reads it in "
+                         "place from the ingest rank's HBM over NVLink (CUDA IPC); 'nccl': dist.broadcast")
     ap.add_argument("--no-frame", action="store_true", help="skip the whole-frame (mapping + post-process) block")
     ap.add_argument("--l2", default="ring", choices=["ring", "flush", "none"],
                     help="ring: the timed steps cycle through distinct device-resident scans whose total "
@@ -359,11 +362,24 @@ def main():
         all_scans = [probe] + [syn.make_scan(wl, base + k) for k in range(1, n_dev)]
         host = all_scans[:n_ring]
         dev_scans, pin_scans = [], []
-        for s in all_scans:
-            d = dict(xyzw=torch.from_numpy(s["xyzw"]).to(dev),
-                     intensity=None if not has_i else torch.from_numpy(s["intensity"]).to(dev),
-                     rgb=None if not has_c else torch.from_numpy(s["rgb"]).to(dev))
-            dev_scans.append(fd.PointCloud(d["xyzw"], d["intensity"], d["rgb"]))
+        peer = sharded and args.transport == "peer"
+        ring = None
+        if peer:
+            # the scans live ONCE, in the ingest rank's HBM; every other rank maps them (CUDA IPC)
+            # and its kernels read them across NVLink while binning: no per-scan collective
+            from fastdem_b200.sharded import PeerScanRing
+            ring = PeerScanRing(n_dev, n, has_i, has_c, device=local_rank, src=0)
+            for j, s in enumerate(all_scans):
+                ring.fill(j, s["xyzw"], s["intensity"], s["rgb"])
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            dev_scans = [ring.cloud(j, n) for j in range(n_dev)]
+        else:
+            for s in all_scans:
+                d = dict(xyzw=torch.from_numpy(s["xyzw"]).to(dev),
+                         intensity=None if not has_i else torch.from_numpy(s["intensity"]).to(dev),
+                         rgb=None if not has_c else torch.from_numpy(s["rgb"]).to(dev))
+                dev_scans.append(fd.PointCloud(d["xyzw"], d["intensity"], d["rgb"]))
         all_scans = None
         for s in host:
             p = dict(xyzw=torch.from_numpy(s["xyzw"]).pin_memory(),
@@ -389,7 +405,10 @@ def main():
         for kk in range(min(4096, args.warmup + 4 * args.steps + 200)):
             pose_of(kk)
 
-        if sharded:
+        if peer:
+            def submit_dev(kk):
+                dem.integrate_async(dev_scans[kk % n_dev], *pose_of(kk))
+        elif sharded:
             # every rank needs the scan: rank 0 (the ingest rank) broadcasts it over NCCL/NVLink
             # inside the timed step; the other ranks integrate out of their receive buffers
             rx = dev_scans[0]
@@ -499,7 +518,19 @@ def main():
         #    form submit(k+1); collect(k) lets the copy of the next scan overlap the kernels of
         #    the current one (double-buffered staging on a copy stream inside the library) ──
         e2e_steps = args.steps
-        if sharded:
+        if peer:
+            # host scan on the ingest rank -> a ring slot in its HBM -> barrier -> every stripe
+            # integrates straight out of that slot (peer reads); the next barrier also keeps the
+            # ingest rank from rewriting a slot a stripe may still be reading
+            def e2e_step(kk):
+                if rank == 0:
+                    pp_ = pin_scans[kk % n_ring]._pinned
+                    ring.fill(kk % n_dev, pp_["xyzw"], pp_["intensity"] if has_i else None,
+                              pp_["rgb"] if has_c else None)
+                    torch.cuda.synchronize(dev)
+                dist.barrier()
+                return dem.integrate_stats(dev_scans[kk % n_dev], *pose_of(kk))
+        elif sharded:
             # host scan on the ingest rank -> its GPU -> NCCL broadcast -> every stripe integrates;
             # the per-step result read is the stats of this rank's stripe
             def e2e_step(kk):
@@ -516,9 +547,11 @@ def main():
                 if has_c:
                     dist.broadcast(rx.color, src=0)
                 return dem.integrate_stats(rx, *pose_of(kk))
-            rx = fd.PointCloud(torch.empty_like(dev_scans[0].xyzw),
-                               None if not has_i else torch.empty_like(dev_scans[0].intensity),
-                               None if not has_c else torch.empty_like(dev_scans[0].color))
+        if sharded:
+            if not peer:
+                rx = fd.PointCloud(torch.empty_like(dev_scans[0].xyzw),
+                                   None if not has_i else torch.empty_like(dev_scans[0].intensity),
+                                   None if not has_c else torch.empty_like(dev_scans[0].color))
             for _ in range(3):
                 e2e_step(k)
                 k += 1
@@ -557,7 +590,7 @@ def main():
             e2e_sync_s = time.perf_counter() - t0
         # context: what the PCIe link does for this scan size (pinned H2D, CUDA events)
         hb = pin_scans[0]._pinned["xyzw"]
-        db_ = torch.empty_like(dev_scans[0].xyzw)
+        db_ = torch.empty((n, 4), dtype=torch.float32, device=dev)
         for _ in range(3):
             db_.copy_(hb, non_blocking=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -642,7 +675,9 @@ def main():
             "config": {"workload": wl.name, "description": wl.description, "points_per_scan": n,
                        "arithmetic": "float32 cell state and point math, float64 grid geometry (as the reference)",
                        "map_cells": int(round(wl.map_width / wl.resolution)) * int(round(wl.map_height / wl.resolution)),
-                       "parallelism": ("row-stripes x%d" % world) if sharded else ("replicas x%d" % world),
+                       "parallelism": ("row-stripes x%d, scan read in place from the ingest GPU over NVLink (CUDA IPC)" % world
+                                       if peer else "row-stripes x%d, scan broadcast with NCCL" % world) if sharded
+                       else ("replicas x%d" % world),
                        "l2": {"ring": f"inputs larger than L2: {n_dev} distinct device-resident scans = "
                                       f"{n_dev * scan_bytes >> 20} MiB cycled (> 126 MiB L2); map state stays warm; "
                                       "steps back to back, one CUDA-event pair",

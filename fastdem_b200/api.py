@@ -74,10 +74,24 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+class DeviceArray:
+    """A raw device buffer (this GPU's or a peer's mapped through CUDA IPC) holding `n` rows of
+    a cloud channel: what the sharded driver passes when the scan lives in another rank's HBM.
+    Assign instances directly to PointCloud.xyzw / .intensity / .color."""
+    __slots__ = ("addr", "shape", "owner")
+
+    def __init__(self, addr: int, n_rows: int, n_cols: int = 1, owner=None):
+        self.addr = int(addr)
+        self.shape = (int(n_rows), int(n_cols))
+        self.owner = owner
+
+
 def _ptr(x, dtype, shape_last: Optional[int] = None):
     """(address, keepalive, n_rows) of a numpy array or torch tensor as contiguous `dtype`."""
     if x is None:
         return None, None, 0
+    if type(x) is DeviceArray:
+        return x.addr, x, x.shape[0]
     if _is_torch(x):
         import torch
         tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]

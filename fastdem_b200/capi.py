@@ -65,6 +65,10 @@ class FdemGeometry(C.Structure):
 
 _P = C.c_void_p
 _ST = C.c_int32
+class FdemIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64), ("size", C.c_uint64)]
+
+
 _f32p, _u8p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p  # addresses are passed as plain ints
 
 # name -> (restype, argtypes); every symbol include/fastdem_b200.h declares
@@ -126,6 +130,11 @@ SIGNATURES = {
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "fdem_map_pointcloud2_field": (_ST, [_P, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_uint32)]),
     "fdem_map_pointcloud2_data": (_ST, [_P, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdem_device_alloc": (_ST, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fdem_device_free": (_ST, [C.c_int32, C.c_void_p]),
+    "fdem_ipc_export": (_ST, [C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(FdemIpcHandle)]),
+    "fdem_ipc_import": (_ST, [C.c_int32, C.POINTER(FdemIpcHandle), C.POINTER(C.c_void_p)]),
+    "fdem_ipc_close": (_ST, [C.c_int32, C.c_void_p]),
     "fdem_uncertainty_fusion": (_ST, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "fdem_feature_extraction": (_ST, [_P, C.c_float, C.c_int32, C.c_float, C.c_float]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),

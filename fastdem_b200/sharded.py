@@ -239,3 +239,100 @@ class ShardedGlobalMap:
             nxt[fill] = (total[fill] / count[fill].astype(np.float32)).astype(np.float32)
             cur = nxt
         return cur
+
+
+class PeerScanRing:
+    """A ring of scan slots in the INGEST rank's HBM that every rank reads in place.
+
+    The ingest rank allocates the slots (fdem_device_alloc), exports them (CUDA IPC) and
+    broadcasts the 72-byte handles once; the other ranks map them (peer access over NVLink /
+    NVSwitch) and hand the mapped pointers to integrate(): K1 and the scatter kernel pull the
+    points across the link while they bin them, so distributing a scan costs no collective and
+    no extra copy — the transfer is fused into the first kernel that needs the data.  Slot
+    layout: xyzw (n x 16 B) | intensity (n x 4 B) | rgb (n x 3 B), each 256-byte aligned.
+
+    Ordering is the caller's: a slot must not be rewritten while a rank may still read it (the
+    bench fills the ring once; the host->device e2e path brackets every step with a barrier)."""
+
+    def __init__(self, n_slots: int, max_points: int, has_intensity: bool, has_color: bool, *,
+                 device: int, src: int = 0, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import api, capi
+        self._api, self._capi, self._C = api, capi, C
+        self.lib = capi.load_library()
+        self.device, self.src = device, src
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_slots, self.max_points = n_slots, max_points
+        self.has_i, self.has_c = has_intensity, has_color
+        al = lambda b: (b + 255) // 256 * 256
+        self.off_i = al(max_points * 16)
+        self.off_c = self.off_i + (al(max_points * 4) if has_intensity else 0)
+        self.slot_bytes = self.off_c + (al(max_points * 3) if has_color else 0)
+        self.base = []          # device address of every slot in THIS process
+        self._owned = self.rank == src
+        handles = []
+        if self._owned:
+            for _ in range(n_slots):
+                p = C.c_void_p()
+                capi.check(self.lib.fdem_device_alloc(device, self.slot_bytes, C.byref(p)))
+                self.base.append(p.value)
+                h = capi.FdemIpcHandle()
+                capi.check(self.lib.fdem_ipc_export(device, p, self.slot_bytes, C.byref(h)))
+                handles.append(bytes(h))
+        if self.world > 1:
+            box = [handles]
+            dist.broadcast_object_list(box, src=src, group=group)
+            handles = box[0]
+            if not self._owned:
+                for hb in handles:
+                    h = capi.FdemIpcHandle.from_buffer_copy(hb)
+                    p = C.c_void_p()
+                    capi.check(self.lib.fdem_ipc_import(device, C.byref(h), C.byref(p)))
+                    self.base.append(p.value)
+
+    def cloud(self, slot: int, n_points: int):
+        """PointCloud whose channels point into ring slot `slot` (valid on every rank)."""
+        api = self._api
+        b = self.base[slot % self.n_slots]
+        pc = api.PointCloud()
+        pc.xyzw = api.DeviceArray(b, n_points, 4, self)
+        pc.intensity = api.DeviceArray(b + self.off_i, n_points, 1, self) if self.has_i else None
+        pc.color = api.DeviceArray(b + self.off_c, n_points, 3, self) if self.has_c else None
+        return pc
+
+    def fill(self, slot: int, xyzw, intensity=None, rgb=None, stream=None):
+        """Ingest rank only: copy one scan (numpy / pinned torch / CUDA torch) into a slot."""
+        if not self._owned:
+            return
+        import torch
+        b = self.base[slot % self.n_slots]
+
+        def view(addr, shape, typestr, dtype):
+            class _H:  # __cuda_array_interface__ provider for a buffer this process owns
+                pass
+            h = _H()
+            h.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (addr, False), "version": 3}
+            h._ring = self
+            return torch.as_tensor(h, device=torch.device("cuda", self.device), dtype=dtype)
+
+        def put(dst, src_):
+            t = src_ if torch.is_tensor(src_) else torch.from_numpy(np.ascontiguousarray(src_))
+            dst.copy_(t, non_blocking=True)
+
+        n = int(xyzw.shape[0])
+        put(view(b, (n, 4), "<f4", torch.float32), xyzw)
+        if self.has_i:
+            put(view(b + self.off_i, (n,), "<f4", torch.float32), intensity)
+        if self.has_c:
+            put(view(b + self.off_c, (n, 3), "|u1", torch.uint8), rgb)
+
+    def close(self):
+        C = self._C
+        for p in self.base:
+            if self._owned:
+                self.lib.fdem_device_free(self.device, C.c_void_p(p))
+            else:
+                self.lib.fdem_ipc_close(self.device, C.c_void_p(p))
+        self.base = []

@@ -323,6 +323,24 @@ fdem_status fdem_map_pointcloud2_field(fdem_map* map, int32_t i, char* buf, int3
                                        uint32_t* offset);
 fdem_status fdem_map_pointcloud2_data(fdem_map* map, uint8_t* dst, const uint8_t** device_ptr);
 
+/* ── multi-GPU plumbing (no counterpart in the single-process reference) ──
+ * One process per GPU.  A scan that every row stripe needs lives ONCE, in the ingest rank's
+ * HBM; the other ranks map that buffer (CUDA IPC, peer access over NVLink / NVSwitch) and pass
+ * the mapped pointer to fdem_mapper_integrate*: K1 and the scatter kernel then read the points
+ * straight out of the peer's memory while they bin them — the "broadcast" is fused into the
+ * first kernel that needs the data instead of being a collective of its own. */
+typedef struct fdem_ipc_handle {
+  uint8_t bytes[64]; /* cudaIpcMemHandle_t */
+  uint64_t size;
+} fdem_ipc_handle;
+fdem_status fdem_device_alloc(int32_t device, size_t bytes, void** ptr);
+fdem_status fdem_device_free(int32_t device, void* ptr);
+/* `ptr` must come from fdem_device_alloc (IPC handles name whole allocations) */
+fdem_status fdem_ipc_export(int32_t device, const void* ptr, size_t bytes, fdem_ipc_handle* out);
+/* maps the exporting process's buffer into this process; enables peer access on first use */
+fdem_status fdem_ipc_import(int32_t device, const fdem_ipc_handle* h, void** ptr);
+fdem_status fdem_ipc_close(int32_t device, void* ptr);
+
 /* ── instrumentation ──────────────────────────────────────────────────────── */
 /* pipeline stages of one scan, in stream order */
 enum {
