@@ -612,6 +612,21 @@ class FastDEM:
             Twb.p, C.byref(stats)))
         return stats
 
+    def submit_pointcloud2(self, msg: "PointCloud2", T_base_sensor, T_world_base) -> int:
+        """Streaming form of integrate_pointcloud2: returns a ticket for collect()."""
+        c = getattr(msg, "_abi_cache", None)
+        if c is None or c[0] is not msg.data:
+            p, keep, _ = _ptr(msg.data, np.uint8)
+            c = (msg.data, p, keep, msg.layout(), msg.size())
+            msg._abi_cache = c
+        Tbs, Twb = _iso(T_base_sensor), _iso(T_world_base)
+        t = C.c_uint64()
+        check(self._lib.fdem_mapper_submit_pointcloud2(self._h, c[1], c[4], C.byref(c[3]), Tbs.p, Twb.p, C.byref(t)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[t.value] = c
+        return t.value
+
     def _channels(self, cloud: PointCloud):
         # pointers of a cloud's channels are cached on the cloud (keyed by the identity of the
         # channel objects): extracting them costs ~3 us per channel

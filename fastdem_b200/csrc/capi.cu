@@ -584,6 +584,12 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
     // K1 unpacks the channels into the staging slot's SoA buffers for the later kernels
     if (lo.off_intensity >= 0) { pp.out_intensity = mp->d_in_intensity[slot]; inten_v = pp.out_intensity; }
     if (lo.off_rgb >= 0) { pp.out_rgb = mp->d_in_rgb[slot]; rgb_v = pp.out_rgb; }
+    // exactly one 4-byte channel in the fourth word (float32 intensity or packed rgb)
+    const bool one_channel = (lo.off_intensity == 12 && lo.intensity_type == 7 && lo.off_rgb < 0) ||
+                             (lo.off_rgb == 12 && lo.off_intensity < 0) ||
+                             (lo.off_intensity < 0 && lo.off_rgb < 0);
+    pp.raw_vec16 = (lo.point_step == 16 && lo.off_x == 0 && lo.off_y == 4 && lo.off_z == 8 && one_channel &&
+                    (reinterpret_cast<uintptr_t>(raw_v) & 15) == 0) ? 1 : 0;
   }
   FDEM_TRY(stage_in(in.xyzw, mp->d_in_xyzw[slot], static_cast<size_t>(n) * 16, &xyzw_v));
   if (!in.raw) {
@@ -1475,6 +1481,10 @@ fdem_status fdem_mapper_integrate_with_cov(fdem_mapper* mp, const float* xyzw, c
   return finish_scan(mp, stats);
 }
 
+static fdem_status enqueue_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
+                                       const fdem_pointcloud2_layout* lo, const double* Tbs,
+                                       const double* Twb);
+
 fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
                                               const fdem_pointcloud2_layout* lo, const double* Tbs,
                                               const double* Twb, fdem_scan_stats* stats) {
@@ -1487,6 +1497,29 @@ fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* da
     if (stats) *stats = mp->last;
     return FDEM_OK;
   }
+  FDEM_TRY(enqueue_pointcloud2(mp, data, n, lo, Tbs, Twb));
+  return finish_scan(mp, stats);
+}
+
+fdem_status fdem_mapper_submit_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
+                                           const fdem_pointcloud2_layout* lo, const double* Tbs,
+                                           const double* Twb, uint64_t* ticket) {
+  FDEM_REQUIRE(mp && lo && Tbs && Twb && ticket, "null argument");
+  FDEM_REQUIRE(n > 0 && lo->off_x >= 0 && lo->off_y >= 0 && lo->off_z >= 0,
+               "submit needs a non-empty cloud with x/y/z fields (integrate() returns false otherwise)");
+  DeviceGuard dg(mp->map->device);
+  const uint64_t before = mp->map->seq;
+  // never let the ring wrap over a result nobody has been able to collect yet
+  if (before >= kResultRing)
+    FDEM_CUDA_TRY(cudaEventSynchronize(mp->map->ev_scan[(before - kResultRing + 1) % kResultRing]));
+  FDEM_TRY(enqueue_pointcloud2(mp, data, n, lo, Tbs, Twb));
+  *ticket = before;
+  return FDEM_OK;
+}
+
+static fdem_status enqueue_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
+                                       const fdem_pointcloud2_layout* lo, const double* Tbs,
+                                       const double* Twb) {
   FDEM_REQUIRE(data, "data is null");
   FDEM_REQUIRE(lo->point_step >= 12 && (lo->point_step & 3) == 0, "point_step must be a multiple of 4");
   auto fits = [&](int32_t off, int32_t size) { return off >= 0 && off + size <= static_cast<int32_t>(lo->point_step); };
@@ -1510,8 +1543,7 @@ fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* da
   in.Twb = Twb;
   in.robot_x = Twb[12];
   in.robot_y = Twb[13];
-  FDEM_TRY(enqueue_scan(mp, in));
-  return finish_scan(mp, stats);
+  return enqueue_scan(mp, in);
 }
 
 fdem_status fdem_mapper_integrate_async(fdem_mapper* mp, const float* xyzw,

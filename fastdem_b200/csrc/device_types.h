@@ -96,6 +96,7 @@ struct PreprocessParams {
   int32_t intensity_type;  // PointField datatype: 2 UINT8, 4 UINT16, 7 FLOAT32, 8 FLOAT64
   float* out_intensity;
   uint8_t* out_rgb;
+  int32_t raw_vec16;  // 16-byte points with x, y, z at 0, 4, 8 and one 4-byte channel at 12, base 16-B aligned
 };
 
 // pointers to every layer the estimator kernel reads or writes (null when absent)

@@ -148,6 +148,22 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
       // nanopcl::from(msg): x/y/z floats at their field offsets, w = 1; non-finite points are
       // skipped before anything else sees them (bridge/ros/impl.hpp:237-244)
       const uint8_t* pt = p.raw + static_cast<size_t>(i) * p.point_step;
+      if (p.raw_vec16) {
+        // the common driver layout — x, y, z and one 4-byte field in a 16-byte point: ONE
+        // 128-bit load per point, like the xyzw path
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.raw) + i);
+        q.x = v.x; q.y = v.y; q.z = v.z;
+        finite = isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+        q.w = 1.0f;
+        if (p.out_intensity && p.intensity_type == 7) {
+          p.out_intensity[i] = v.w;
+        } else if (p.out_rgb) {
+          const uint32_t rgb = __float_as_uint(v.w);
+          p.out_rgb[static_cast<size_t>(i) * 3 + 0] = static_cast<uint8_t>((rgb >> 16) & 0xFF);
+          p.out_rgb[static_cast<size_t>(i) * 3 + 1] = static_cast<uint8_t>((rgb >> 8) & 0xFF);
+          p.out_rgb[static_cast<size_t>(i) * 3 + 2] = static_cast<uint8_t>(rgb & 0xFF);
+        }
+      } else {
       q.x = __ldg(reinterpret_cast<const float*>(pt + p.off_x));
       q.y = __ldg(reinterpret_cast<const float*>(pt + p.off_y));
       q.z = __ldg(reinterpret_cast<const float*>(pt + p.off_z));
@@ -177,6 +193,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
         p.out_rgb[static_cast<size_t>(i) * 3 + 0] = static_cast<uint8_t>((rgb >> 16) & 0xFF);
         p.out_rgb[static_cast<size_t>(i) * 3 + 1] = static_cast<uint8_t>((rgb >> 8) & 0xFF);
         p.out_rgb[static_cast<size_t>(i) * 3 + 2] = static_cast<uint8_t>(rgb & 0xFF);
+      }
       }
     } else {
       q = __ldg(&p.xyzw[i]);

@@ -255,6 +255,14 @@ fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* m, const uint8_t* dat
                                               const double T_base_sensor[16],
                                               const double T_world_base[16],
                                               fdem_scan_stats* stats);
+/* streaming form (see fdem_mapper_submit): queue the message, collect its stats by ticket; the
+ * copy of message k+1 overlaps the kernels of message k.  A PointCloud2 point is usually
+ * smaller than the Vector4f + intensity the reference unpacks it into (x, y, z, intensity =
+ * 16 bytes instead of 20), so this is also the cheapest way across PCIe. */
+fdem_status fdem_mapper_submit_pointcloud2(fdem_mapper* m, const uint8_t* data, size_t num_points,
+                                           const fdem_pointcloud2_layout* layout,
+                                           const double T_base_sensor[16],
+                                           const double T_world_base[16], uint64_t* ticket);
 
 /* FastDEM::onScanPreprocessed payload (fastdem.cpp:139-141): the preprocessed cloud of the
  * LAST integrate, compacted in input order.  Buffers are HOST memory sized for n_kept:

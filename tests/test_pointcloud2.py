@@ -62,7 +62,8 @@ def test_field_parsing_rgba_and_unknown_fields():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("itype,with_rgb", [(PF_FLOAT32, False), (PF_UINT16, True), (PF_FLOAT64, True), (PF_UINT8, False)])
+@pytest.mark.parametrize("itype,with_rgb", [(PF_FLOAT32, False), (PF_UINT16, True), (PF_FLOAT64, True), (PF_UINT8, False),
+                                            (None, True), (None, False)])   # 16-byte points: the 128-bit load path
 def test_integrate_pointcloud2_matches_oracle(fdem, itype, with_rgb):
     from fastdem_b200 import synthetic as syn
     from parity_utils import compare_maps
@@ -79,9 +80,12 @@ def test_integrate_pointcloud2_matches_oracle(fdem, itype, with_rgb):
         bad = rng.choice(len(xyz), 40, replace=False)
         xyz[bad[:20], 0] = np.nan
         xyz[bad[20:], 2] = np.inf          # +inf survives the default range crop: must go in ingest
-        inten = s["intensity"] * (200 if itype in (PF_UINT8, PF_UINT16) else 1)
+        inten = None if itype is None else s["intensity"] * (200 if itype in (PF_UINT8, PF_UINT16) else 1)
         rgb = rng.randint(0, 256, size=(len(xyz), 3)) if with_rgb else None
-        msg = PointCloud2.from_arrays(xyz, inten, rgb, intensity_type=itype, pad=k % 3 * 4)
+        pad = 0 if itype is None else k % 3 * 4
+        if itype is None and not with_rgb:
+            pad = 4   # x, y, z + 4 bytes of padding: still a 16-byte point, no channel
+        msg = PointCloud2.from_arrays(xyz, inten, rgb, intensity_type=itype or PF_FLOAT32, pad=pad)
         st = gdem.integrate_pointcloud2(msg, s["T_base_sensor"], s["T_world_base"])
         p, i, c = ob.from_pointcloud2(msg.data, msg.size(), msg.layout())
         ok, ost, _ = odem.integrate(p, s["T_base_sensor"], s["T_world_base"], i, c)
@@ -110,3 +114,37 @@ def test_integrate_pointcloud2_degenerate_messages(fdem):
     with pytest.raises(fdem.FdemError):  # a float field that is not 4-byte aligned inside the point
         bad = PointCloud2(np.zeros(64, np.uint8), 4, 1, 16, [("x", 1, 7), ("y", 5, 7), ("z", 9, 7)])
         dem.integrate(bad, np.eye(4), np.eye(4))
+
+
+@pytest.mark.gpu
+def test_submit_pointcloud2_stream_equals_sync(fdem):
+    """submit_pointcloud2(k+1); collect(k) — the streaming form, two messages in flight — must
+    leave the same map as integrate_pointcloud2 one message at a time."""
+    from fastdem_b200 import synthetic as syn
+    from parity_utils import compare_layer
+    wl = syn.WORKLOADS["tiny"]
+    maps = []
+    for streaming in (False, True):
+        gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution)
+        gdem = fdem.FastDEM(gmap, wl.config())
+        msgs = []
+        for k in range(7):
+            s = syn.make_scan(wl, k)
+            msgs.append((PointCloud2.from_arrays(s["xyzw"][:, :3], s["intensity"]), s["T_base_sensor"], s["T_world_base"]))
+        cells = []
+        if streaming:
+            prev = None
+            for m, a, b in msgs:
+                t = gdem.submit_pointcloud2(m, a, b)
+                if prev is not None:
+                    cells.append(gdem.collect(prev).n_cells)
+                prev = t
+            cells.append(gdem.collect(prev).n_cells)
+        else:
+            for m, a, b in msgs:
+                cells.append(gdem.integrate_pointcloud2(m, a, b).n_cells)
+        maps.append((gmap, cells))
+    assert maps[0][1] == maps[1][1] and min(maps[0][1]) > 0
+    for name in maps[0][0].getLayers():
+        compare_layer(name, maps[1][0].get(name), maps[0][0].get(name), rtol=0, atol=0)
+    assert msgs[0][0].point_step == 16   # x, y, z, intensity: 16 bytes per point on the wire
