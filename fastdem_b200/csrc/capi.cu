@@ -197,6 +197,7 @@ struct DeviceGuard {
   bool ok = false;
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    else (void)cudaGetLastError();  // a bad ordinal must not linger as the next call's "last error"
   }
   ~DeviceGuard() {
     if (ok) cudaSetDevice(prev);
