@@ -77,3 +77,49 @@ def test_c5_oracle_parity_global_64m_cells(fdem):
     assert gmap.getSize() == (8000, 8000)
     for layer in ("elevation", "variance", "n_points", "_kalman_p", "obstacle", "intensity", "elevation_max"):
         compare_layer(layer, gmap.get(layer), omap.get(layer))
+
+
+def test_long_stream_soak_matches_oracle(fdem):
+    """600 VLP-16 scans of a moving robot through every entry style in turn — synchronous,
+    queued (integrate_async), streaming host buffers (submit / collect, staging ring and result
+    ring wrap many times), PointCloud2 bodies — with the bucket shape switching on the way.
+    The map must still equal the oracle's, cell for cell, at the end."""
+    import oracle_binding as ob
+    from fastdem_b200.api import PointCloud2
+    wl = syn.WORKLOADS["c1_vlp16_local"]
+    cfg = wl.config()
+    gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
+    gdem = fdem.FastDEM(gmap, cfg)
+    omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    odem = ob.OracleFastDEM(omap, cfg)
+    scans = [syn.make_scan(wl, k) for k in range(12)]
+    clouds = [fdem.PointCloud(s["xyzw"], s["intensity"]) for s in scans]
+    msgs = [PointCloud2.from_arrays(s["xyzw"][:, :3], s["intensity"]) for s in scans]
+    pending = []
+    n_cells_gpu, n_cells_cpu = 0, 0
+    for k in range(600):
+        j = k % len(scans)
+        Tbs, Twb = syn.pose(wl, k)
+        mode = (k // 50) % 4
+        if mode != 2 and mode != 3 and pending:     # leaving a streaming phase: drain
+            n_cells_gpu += sum(gdem.collect(t).n_cells for t in pending)
+            pending = []
+        if mode == 0:
+            n_cells_gpu += gdem.integrate_stats(clouds[j], Tbs, Twb).n_cells
+        elif mode == 1:
+            gdem.integrate_async(clouds[j], Tbs, Twb)
+            if k % 50 == 49:
+                gdem.wait()
+        elif mode == 2:
+            pending.append(gdem.submit(clouds[j], Tbs, Twb))
+        else:
+            pending.append(gdem.submit_pointcloud2(msgs[j], Tbs, Twb))
+        if len(pending) > 3:
+            n_cells_gpu += gdem.collect(pending.pop(0)).n_cells
+        _, ost, _ = odem.integrate(scans[j]["xyzw"], Tbs, Twb, scans[j]["intensity"], None)
+        if mode != 1:
+            n_cells_cpu += ost.n_cells
+    n_cells_gpu += sum(gdem.collect(t).n_cells for t in pending)
+    gdem.wait()
+    assert n_cells_gpu == n_cells_cpu > 100000
+    compare_maps(gmap, omap)
