@@ -7,10 +7,14 @@ A "step" is one integrate() of one synthetic scan of the workload (default: BASE
 configs[1], 64-beam LiDAR 131K pts, 30x30 m @ 0.05 m, Kalman, LOCAL).  One JSON line on
 stdout (rank 0).
 
-  value    scans/s with the scan already resident in HBM (device pointers through the C-ABI,
-           scans queued back to back, no host sync inside the timed region).  L2 is flushed
-           (256 MiB fill) before every timed step, each step is bracketed by CUDA events on
-           the stream the kernels run on, and ms_per_step = mean over the K steps.
+  value    scans/s with the scans already resident in HBM (device pointers through the C-ABI,
+           queued back to back, no host sync inside the timed region), submitted 8 at a time
+           through fdem_mapper_integrate_batch — identical results to 8 integrate() calls, with
+           scan k+1's front half overlapping scan k's estimator (--batch 1: one call per scan;
+           the JSON also carries that figure as value_scan_by_scan).  The timed steps cycle
+           through distinct device-resident scans totalling more than L2 (--l2 flush: a 256 MiB
+           fill before every step instead); one CUDA-event pair on the kernels' stream around
+           the K steps, ms_per_step = that time / K.
   e2e      the same metric through the public API with HOST (pinned) buffers: every step
            copies the scan host->device, runs integrate() synchronously and reads the scan
            stats + committed geometry back.  Wall clock, barrier + synchronize on both sides.
@@ -297,6 +301,9 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="c5_global at N>1: how the stripes get the scan — 'peer': every rank's K1 reads it in "
                          "place from the ingest rank's HBM over NVLink (CUDA IPC); 'nccl': dist.broadcast")
+    ap.add_argument("--batch", type=int, default=8,
+                    help="scans per fdem_mapper_integrate_batch call in the device-resident `value` loop "
+                         "(1 = one fdem_mapper_integrate_async per scan)")
     ap.add_argument("--no-frame", action="store_true", help="skip the whole-frame (mapping + post-process) block")
     ap.add_argument("--l2", default="ring", choices=["ring", "flush", "none"],
                     help="ring: the timed steps cycle through distinct device-resident scans whose total "
@@ -425,6 +432,25 @@ def main():
             def submit_dev(kk):
                 dem.integrate_async(dev_scans[kk % n_dev], *pose_of(kk))
 
+        # Batched submission for the timed `value` loop: S consecutive scans per
+        # fdem_mapper_integrate_batch call (same results as S integrate() calls; scan k+1's front
+        # half overlaps scan k's estimator inside one graph).  Raycasting and the sharded global map
+        # keep the scan-by-scan queue.
+        S = max(1, min(8, args.batch))
+        if sharded or cfg.raycasting_enabled:
+            S = 1
+
+        def submit_many(k0, count):
+            kk = k0
+            while count - (kk - k0) >= S and S > 1:
+                dem.integrate_batch([dev_scans[(kk + j) % n_dev] for j in range(S)],
+                                    [pose_of(kk + j) for j in range(S)], wait=False)
+                kk += S
+            while kk - k0 < count:
+                submit_dev(kk)
+                kk += 1
+            return kk
+
         def barrier():
             torch.cuda.synchronize(dev)
             if distributed:
@@ -439,6 +465,10 @@ def main():
             submit_dev(k)
             k += 1
         dem.wait()
+        if S > 1:   # build the batch graph (and let the bucket shape settle) outside the timed region
+            for _ in range(3):
+                k = submit_many(k, S)
+                dem.wait()
 
         # ── timed region: device-resident inputs, CUDA events on the kernels' stream ──
         sampler.wait_first()
@@ -467,9 +497,7 @@ def main():
             barrier()
             t_cpu0 = time.perf_counter()
             e0.record(stream)
-            for i in range(args.steps):
-                submit_dev(k)
-                k += 1
+            k = submit_many(k, args.steps)
             e1.record(stream)
             cpu_enqueue_s = time.perf_counter() - t_cpu0
             last = dem.wait()
@@ -477,6 +505,20 @@ def main():
             total_ms = float(e0.elapsed_time(e1))
         t_region = (t_cpu0, time.perf_counter())
         launches = dem.launch_count() - l0
+        # the same loop through the per-scan call (what `value` was before batching), for reference
+        value_scan_by_scan = None
+        if S > 1 and args.l2 != "flush":
+            n2 = max(args.steps // 2, 1)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            f0.record(stream)
+            for _ in range(n2):
+                submit_dev(k)
+                k += 1
+            f1.record(stream)
+            dem.wait()
+            barrier()
+            value_scan_by_scan = n2 * (1 if sharded else world) / (float(f0.elapsed_time(f1)) * 1e-3)
         lib_launches = dem.library_launch_count() - lib0
         # keep the identical load running until nvidia-smi has seen >= 1 s of it (same step
         # count on every rank: the sharded mode broadcasts inside each step)
@@ -709,8 +751,12 @@ def main():
                                       "steps back to back, one CUDA-event pair",
                               "flush": "256 MiB L2 flush before every timed step, one CUDA-event pair per step",
                               "none": "no flush, small ring"}[args.l2],
-                       "scan_ring": n_dev},
+                       "scan_ring": n_dev,
+                       "submission": (f"fdem_mapper_integrate_batch, {S} scans per call (results identical to {S} "
+                                      "integrate() calls; scan k+1's front half overlaps scan k's estimator)")
+                       if S > 1 else "one fdem_mapper_integrate_async per scan"},
             "cpu_enqueue_us_per_step": 1e6 * cpu_enqueue_s / args.steps,
+            "value_scan_by_scan": value_scan_by_scan,
             "e2e": {"value": e2e_value, "unit": "scans/s", "mpoints_per_s": e2e_value * n / 1e6,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32 + 88,

@@ -671,6 +671,45 @@ class FastDEM:
             Twb.p))
         self._keep = keep
 
+    def integrate_batch(self, clouds, poses, wait: bool = True):
+        """Up to 8 consecutive integrate() calls as one graph in which scan k+1's front half runs
+        beside scan k's estimator (fdem_mapper_integrate_batch).  clouds: list of PointCloud;
+        poses: list of (T_base_sensor, T_world_base).  Returns the per-scan stats (wait=True) or
+        None (queued; see wait())."""
+        S = len(clouds)
+        key = tuple(id(c) for c in clouds)
+        caches = getattr(self, "_batch_caches", None)
+        if caches is None:
+            caches = self._batch_caches = {}
+        cache = caches.get(key)
+        if cache is not None and any(a is not b for a, b in zip(cache[11], clouds)):
+            cache = None   # an id() was recycled for a different object
+        if cache is None:
+            ch = [self._channels(c) for c in clouds]
+            has_i = ch[0][2] is not None
+            has_c = ch[0][3] is not None
+            vp = C.c_void_p * S
+            px = vp(*[c[1] for c in ch])
+            pi = vp(*[c[2] for c in ch]) if has_i else None
+            pc = vp(*[c[3] for c in ch]) if has_c else None
+            pn = (C.c_size_t * S)(*[c[0] for c in ch])
+            cache = (key, px, pi, pc, pn, ch, np.empty(S * 16, np.float64), np.empty(S * 16, np.float64),
+                     (FdemScanStats * S)())
+            cache = cache + (cache[6].ctypes.data, cache[7].ctypes.data, list(clouds))
+            if len(caches) >= 256:
+                caches.clear()
+            caches[key] = cache
+        _, px, pi, pc, pn, ch, tbs, twb, stats, ptbs, ptwb, _ = cache
+        for i, (a, b) in enumerate(poses):
+            tbs[16 * i:16 * i + 16] = _iso(a).a
+            twb[16 * i:16 * i + 16] = _iso(b).a
+        check(self._lib.fdem_mapper_integrate_batch(self._h, S, px, pi, pc, pn, ptbs, ptwb,
+                                                    stats if wait else None))
+        if not wait:
+            self._keep = ch
+            return None
+        return [FdemScanStats.from_buffer_copy(st) for st in stats]
+
     def submit(self, cloud: PointCloud, T_base_sensor, T_world_base) -> int:
         """Queue one scan; returns its ticket.  `submit(k+1); collect(k)` overlaps the
         host->device copy of scan k+1 with the kernels of scan k."""

@@ -178,6 +178,18 @@ struct fdem_mapper {
   TileBuffers tb{};
   uint32_t max_buckets = 0;   // bucket arrays are sized for the smallest bucket shape
   bool bucket_bits_auto = true;  // pick the K3t bucket shape from the last scan's density
+  // batched integration (fdem_mapper_integrate_batch): a second scratch set so scan k+1's
+  // front half can run beside scan k's estimator, a ring of state slots, the batch graph
+  float4* d_pm2 = nullptr;
+  uint32_t* d_keys2 = nullptr;
+  uint32_t* d_counters2 = nullptr;
+  TileBuffers tb2{};
+  size_t cap2 = 0;
+  DeviceState* d_ring = nullptr;   // [kMaxBatch + 1]
+  MoveRecord* d_move = nullptr;    // [2]
+  struct BatchGraphState* bg = nullptr;   // [2]: executable graphs used alternately, so one can be
+                                          // re-parameterised while the other is still executing
+  int bg_flip = 0;
   // by-name layer lookups of one scan (~25 string searches), cached until a layer is added
   uint64_t cached_epoch = ~0ull;
   EstLayers cached_L{};
@@ -510,9 +522,13 @@ struct ScanInputs {
   double robot_x, robot_y;
   const uint8_t* raw = nullptr;                    // PointCloud2 body (xyzw etc. null then)
   const fdem_pointcloud2_layout* layout = nullptr;
+  bool known_device = false;                       // the caller has already checked: device pointers
 };
 
-fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
+// build_only: fill *build_only with the scan's kernel arguments (against the primary scratch
+// set, for result slot `ticket_override`) and return without launching anything
+fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* build_only = nullptr,
+                         uint64_t ticket_override = 0) {
   fdem_map* m = mp->map;
   const fdem_config& cfg = mp->cfg;
   cudaStream_t s = m->stream;
@@ -544,14 +560,14 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   // slot (ticket % kStageRing) on a separate copy stream, so the copy of scan k+1 overlaps
   // the kernels of scan k; the compute stream waits for the copy through an event.
   FDEM_REQUIRE(!(in.cov9 && in.var_z), "cov9 and var_z are exclusive");
-  const uint64_t ticket = m->seq;
+  const uint64_t ticket = build_only ? ticket_override : m->seq;
   const int slot = static_cast<int>(ticket % kStageRing);
   const bool overlap = !mp->stage_timing;  // stage timing wants the copy on the timed stream
   cudaStream_t cs = overlap ? mp->copy_stream : s;
   bool staged = false;
   auto stage_in = [&](const void* src, void* scratch, size_t bytes, const void** out) -> fdem_status {
     if (!src) { *out = nullptr; return FDEM_OK; }
-    if (is_device_pointer(src)) { *out = src; return FDEM_OK; }
+    if (in.known_device || is_device_pointer(src)) { *out = src; return FDEM_OK; }
     if (!staged && overlap && ticket >= kStageRing) {
       // the slot's previous user (scan ticket - kStageRing) must be done with the buffers
       FDEM_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_scan[(ticket - kStageRing) % kResultRing], 0));
@@ -738,6 +754,10 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in) {
   L.pub.enabled = (tile && !raycast) ? 1 : 0;
   L.pub.st_cur = m->d_state;
   L.pub.host_out = host_slot;
+  if (build_only) {
+    *build_only = L;
+    return FDEM_OK;
+  }
   const bool graph = tile && mp->use_graph && !mp->stage_timing && !raycast;
   fdem_status launch_status = FDEM_OK;
   if (graph) {
@@ -904,6 +924,197 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
     }
     G.cached = L;
   }
+  FDEM_CUDA_TRY(cudaGraphLaunch(G.exec, s));
+  return FDEM_OK;
+}
+
+// ── batched integration: S scans in ONE graph whose DAG lets scan k+1's front half (K1,
+// commit, scatter — they touch only scan scratch and the geometry chain) run beside scan k's
+// back half (back prologue + K3t — everything that writes the map).  Edges:
+//   K1_i -> K2_i -> SC_i -> BP_i -> K3_i      (one scan)
+//   K2_i -> K1_{i+1}                           (geometry after scan i's move)
+//   K3_i -> BP_{i+1}                           (map layers, touched list)
+//   K3_i -> K1_{i+2}                           (scratch set i & 1 is free again)
+constexpr int kMaxBatch = 8;   // = kResultRing: every scan of a batch has its own result slot
+enum { BN_K1 = 0, BN_K2, BN_SC, BN_BP, BN_K3, BN_COUNT };
+
+struct BatchScan {
+  ScanLaunch L;
+  BackParams bp;
+  uint32_t n;
+};
+
+}  // namespace
+
+struct BatchGraphState {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node[kMaxBatch][BN_COUNT] = {};
+  int S = 0;
+  uint32_t tile_shape_key = 0;  // bucket bits the graph was built for
+  BatchScan scan[kMaxBatch];    // this batch's kernel arguments
+  BatchScan cached[kMaxBatch];  // what the executable graph currently holds
+};
+
+namespace {
+
+void destroy_batch_graph(fdem_mapper* mp) {
+  if (!mp->bg) return;
+  for (int k = 0; k < 2; ++k) {
+    if (mp->bg[k].exec) cudaGraphExecDestroy(mp->bg[k].exec);
+    if (mp->bg[k].graph) cudaGraphDestroy(mp->bg[k].graph);
+  }
+  delete[] mp->bg;
+  mp->bg = nullptr;
+}
+
+fdem_status ensure_batch_scratch(fdem_mapper* mp) {
+  fdem_map* m = mp->map;
+  if (!mp->d_ring) {
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_ring, (kMaxBatch + 1) * sizeof(DeviceState)));
+    FDEM_CUDA_TRY(cudaMemset(mp->d_ring, 0, (kMaxBatch + 1) * sizeof(DeviceState)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_move, 2 * sizeof(MoveRecord)));
+    FDEM_CUDA_TRY(cudaMemset(mp->d_move, 0, 2 * sizeof(MoveRecord)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_counters2, CNT_COUNT * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMemset(mp->d_counters2, 0, CNT_COUNT * sizeof(uint32_t)));
+    const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_count, nb));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_offset, nb));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_cursor, nb));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_list, nb * 4));
+    FDEM_CUDA_TRY(cudaMemset(mp->tb2.bucket_count, 0, nb));
+    FDEM_CUDA_TRY(cudaMemset(mp->tb2.bucket_cursor, 0, nb));
+  }
+  if (mp->cap2 < mp->cap) {
+    FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cudaFree(mp->d_pm2);
+    cudaFree(mp->d_keys2);
+    cudaFree(mp->tb2.records);
+    mp->d_pm2 = nullptr; mp->d_keys2 = nullptr; mp->tb2.records = nullptr;
+    mp->cap2 = 0;
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_pm2, mp->cap * sizeof(float4)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_keys2, mp->cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.records, mp->cap * sizeof(CellRecord)));
+    mp->cap2 = mp->cap;
+  }
+  return FDEM_OK;
+}
+
+// point scan i's kernel arguments (built against the primary scratch set) at scratch set
+// i & 1, its slots of the state ring, and the deferred-commit / back-prologue split
+void retarget_for_batch(fdem_mapper* mp, int i, BatchScan& b) {
+  fdem_map* m = mp->map;
+  ScanLaunch& L = b.L;
+  const int q = i & 1;
+  TileBuffers tb = q ? mp->tb2 : mp->tb;
+  tb.n_buckets = mp->tb.n_buckets;
+  tb.bucket_bits = mp->tb.bucket_bits;
+  float4* pm = q ? mp->d_pm2 : mp->d_pm;
+  uint32_t* keys = q ? mp->d_keys2 : mp->d_keys;
+  uint32_t* counters = q ? mp->d_counters2 : mp->d_counters;
+  const DeviceState* st_in = i == 0 ? m->d_state : mp->d_ring + i;
+  DeviceState* st_out = mp->d_ring + i + 1;
+  L.pp.bucket_count = tb.bucket_count;
+  L.pm = pm; L.keys = keys; L.counters = counters;
+  L.st_cur = st_in;            // K1 / K2 read the geometry the previous scan's commit left
+  L.st_next = st_out;
+  L.cp.tb = tb;
+  L.cp.defer = 1;
+  L.cp.move_out = mp->d_move + q;
+  L.cp.obstacle = nullptr;
+  L.sp.keys = keys; L.sp.pm = pm; L.sp.tb = tb; L.sp.counters = counters;
+  L.sp.obstacle = nullptr;     // the back prologue resets the obstacle cells
+  L.ep.pm = pm;
+  L.tb = tb;
+  L.pub.enabled = 1;
+  L.pub.st_cur = m->d_state;   // publish keeps the map's current state up to date per scan
+  b.bp = BackParams{};
+  b.bp.counters = counters;
+  b.bp.st_cur = m->d_state;
+  b.bp.st_out = st_out;
+  b.bp.move = mp->d_move + q;
+  b.bp.obstacle = L.ep.L.obstacle;
+  b.bp.touched_keys = m->d_touched_keys;
+  b.bp.invalid_key = L.pp.invalid_key;
+  b.bp.clear_policy = L.cp.clear_policy;
+}
+
+void batch_node_args(BatchScan& b, NodeArgs out[BN_COUNT]) {
+  ScanLaunch& L = b.L;
+  out[BN_K1].d = desc_preprocess_bin(b.n);
+  out[BN_K1].args[0] = &L.pp; out[BN_K1].args[1] = &L.st_cur; out[BN_K1].args[2] = &L.counters;
+  out[BN_K1].args[3] = &L.pm; out[BN_K1].args[4] = &L.keys; out[BN_K1].args[5] = &L.vals;
+  out[BN_K2].d = desc_commit();
+  out[BN_K2].args[0] = &L.cp; out[BN_K2].args[1] = &L.st_cur; out[BN_K2].args[2] = &L.st_next;
+  out[BN_K2].args[3] = &L.counters; out[BN_K2].args[4] = &L.lt;
+  out[BN_SC].d = desc_scatter_records(b.n);
+  out[BN_SC].args[0] = &L.sp;
+  out[BN_BP].d = desc_back_prologue();
+  out[BN_BP].args[0] = &b.bp; out[BN_BP].args[1] = &L.lt;
+  out[BN_K3].d = desc_tile_estimate(L.tb.n_buckets, L.tb.bucket_bits);
+  out[BN_K3].args[0] = &L.ep; out[BN_K3].args[1] = &L.tb; out[BN_K3].args[2] = &L.counters;
+  out[BN_K3].args[3] = &L.st_next; out[BN_K3].args[4] = &L.pub;
+}
+
+fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
+  BatchGraphState& G = mp->bg[mp->bg_flip];
+  const bool rebuild = !G.exec || G.S != S || G.tile_shape_key != mp->tb.bucket_bits;
+  if (rebuild) {
+    if (G.exec) cudaGraphExecDestroy(G.exec);
+    if (G.graph) cudaGraphDestroy(G.graph);
+    G.exec = nullptr; G.graph = nullptr;
+    FDEM_CUDA_TRY(cudaGraphCreate(&G.graph, 0));
+    for (int i = 0; i < S; ++i) {
+      NodeArgs na[BN_COUNT];
+      batch_node_args(G.scan[i], na);
+      for (int k = 0; k < BN_COUNT; ++k) {
+        cudaKernelNodeParams kp = node_params(na[k]);
+        FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i][k], G.graph, nullptr, 0, &kp));
+      }
+    }
+    auto edge = [&](cudaGraphNode_t a, cudaGraphNode_t b) -> cudaError_t {
+      return cudaGraphAddDependencies(G.graph, &a, &b, 1);
+    };
+    for (int i = 0; i < S; ++i) {
+      for (int k = 1; k < BN_COUNT; ++k) FDEM_CUDA_TRY(edge(G.node[i][k - 1], G.node[i][k]));
+      if (i + 1 < S) {
+        FDEM_CUDA_TRY(edge(G.node[i][BN_K2], G.node[i + 1][BN_K1]));
+        FDEM_CUDA_TRY(edge(G.node[i][BN_K3], G.node[i + 1][BN_BP]));
+      }
+      if (i + 2 < S) FDEM_CUDA_TRY(edge(G.node[i][BN_K3], G.node[i + 2][BN_K1]));
+    }
+    FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
+    G.S = S;
+    G.tile_shape_key = mp->tb.bucket_bits;
+  } else {
+    // patch only the nodes whose arguments differ from what the executable graph holds
+    for (int i = 0; i < S; ++i) {
+      const BatchScan& c = G.cached[i];
+      const BatchScan& b = G.scan[i];
+      const ScanLaunch& L = b.L;
+      const ScanLaunch& C = c.L;
+      const bool shared = L.st_cur != C.st_cur || L.st_next != C.st_next || L.counters != C.counters ||
+                          L.pm != C.pm || L.keys != C.keys || L.vals != C.vals || b.n != c.n ||
+                          std::memcmp(&L.tb, &C.tb, sizeof(TileBuffers)) != 0;
+      bool dirty[BN_COUNT];
+      dirty[BN_K1] = shared || std::memcmp(&L.pp, &C.pp, sizeof(L.pp)) != 0;
+      dirty[BN_K2] = shared || std::memcmp(&L.cp, &C.cp, sizeof(L.cp)) != 0 ||
+                     std::memcmp(&L.lt, &C.lt, sizeof(L.lt)) != 0;
+      dirty[BN_SC] = shared || std::memcmp(&L.sp, &C.sp, sizeof(L.sp)) != 0;
+      dirty[BN_BP] = shared || std::memcmp(&b.bp, &c.bp, sizeof(b.bp)) != 0 ||
+                     std::memcmp(&L.lt, &C.lt, sizeof(L.lt)) != 0;
+      dirty[BN_K3] = shared || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0 ||
+                     std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
+      NodeArgs na[BN_COUNT];
+      batch_node_args(G.scan[i], na);
+      for (int k = 0; k < BN_COUNT; ++k) {
+        if (!dirty[k]) continue;
+        cudaKernelNodeParams kp = node_params(na[k]);
+        FDEM_CUDA_TRY(cudaGraphExecKernelNodeSetParams(G.exec, G.node[i][k], &kp));
+      }
+    }
+  }
+  for (int i = 0; i < S; ++i) G.cached[i] = G.scan[i];
   FDEM_CUDA_TRY(cudaGraphLaunch(G.exec, s));
   return FDEM_OK;
 }
@@ -1407,6 +1618,17 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   if (mp->copy_stream) cudaStreamSynchronize(mp->copy_stream);
   free_scratch(mp);
   destroy_scan_graph(mp);
+  destroy_batch_graph(mp);
+  cudaFree(mp->d_pm2);
+  cudaFree(mp->d_keys2);
+  cudaFree(mp->d_counters2);
+  cudaFree(mp->tb2.records);
+  cudaFree(mp->tb2.bucket_count);
+  cudaFree(mp->tb2.bucket_offset);
+  cudaFree(mp->tb2.bucket_cursor);
+  cudaFree(mp->tb2.bucket_list);
+  cudaFree(mp->d_ring);
+  cudaFree(mp->d_move);
   for (cudaEvent_t e : mp->ev_copied)
     if (e) cudaEventDestroy(e);
   if (mp->copy_stream) cudaStreamDestroy(mp->copy_stream);
@@ -1590,6 +1812,90 @@ fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stat
   if (stats->n_cells > 0) m->obstacle_full_clear = false;
   adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
   return FDEM_OK;
+}
+
+fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const float* const* xyzw,
+                                        const float* const* intensity, const uint8_t* const* rgb,
+                                        const size_t* n_points, const double* Tbs, const double* Twb,
+                                        fdem_scan_stats* stats) {
+  FDEM_REQUIRE(mp && xyzw && n_points && Tbs && Twb, "null argument");
+  FDEM_REQUIRE(n_scans >= 1 && n_scans <= kMaxBatch, "a batch holds 1 to 8 scans");
+  fdem_map* m = mp->map;
+  DeviceGuard dg(m->device);
+  const bool overlapped = mp->use_tile && mp->use_graph && !mp->stage_timing && !mp->cfg.raycasting_enabled;
+  bool on_device = true;
+  for (int i = 0; i < n_scans; ++i) {
+    FDEM_REQUIRE(n_points[i] > 0 && xyzw[i], "every scan of a batch must be non-empty");
+    on_device = on_device && is_device_pointer(xyzw[i]) && (!intensity || !intensity[i] || is_device_pointer(intensity[i])) &&
+                (!rgb || !rgb[i] || is_device_pointer(rgb[i]));
+  }
+  if (!overlapped || !on_device) {
+    // same results, one scan after the other (raycasting, the global-sort path and host input
+    // buffers keep the per-scan pipeline)
+    for (int i = 0; i < n_scans; ++i) {
+      FDEM_TRY(integrate_common(mp, xyzw[i], nullptr, intensity ? intensity[i] : nullptr, rgb ? rgb[i] : nullptr,
+                                n_points[i], Tbs + 16 * i, Twb + 16 * i));
+      FDEM_TRY(finish_scan(mp, stats ? stats + i : nullptr));
+    }
+    return FDEM_OK;
+  }
+  cudaStream_t s = m->stream;
+  size_t n_max = 0;
+  for (int i = 0; i < n_scans; ++i) n_max = std::max(n_max, n_points[i]);
+  FDEM_TRY(ensure_capacity(mp, n_max));
+  FDEM_TRY(ensure_batch_scratch(mp));
+  if (!mp->bg) mp->bg = new (std::nothrow) BatchGraphState[2]();
+  mp->bg_flip ^= 1;
+  if (!mp->bg) return set_error(FDEM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  // Result slots are reused every kResultRing scans.  A batch hands out no tickets, so nobody
+  // can still want an older slot's content: no wait here (the host keeps queueing batches while
+  // the device works; fdem_mapper_wait reads the newest slot after a stream sync).
+  const uint64_t ticket0 = m->seq;
+  for (int i = 0; i < n_scans; ++i) {
+    ScanInputs in{};
+    in.xyzw = xyzw[i];
+    in.intensity = intensity ? intensity[i] : nullptr;
+    in.rgb = rgb ? rgb[i] : nullptr;
+    in.n = n_points[i];
+    in.input_frame = INPUT_SENSOR_FRAME;
+    in.Tbs = Tbs + 16 * i;
+    in.Twb = Twb + 16 * i;
+    in.robot_x = in.Twb[12];
+    in.robot_y = in.Twb[13];
+    in.known_device = true;
+    BatchScan& b = mp->bg[mp->bg_flip].scan[i];
+    FDEM_TRY(enqueue_scan(mp, in, &b.L, ticket0 + i));
+    b.n = static_cast<uint32_t>(n_points[i]);
+    retarget_for_batch(mp, i, b);
+  }
+  fdem_status st = launch_batch_graph(mp, n_scans, s);
+  if (st != FDEM_OK) {
+    mp->tile_dirty = true;
+    mp->counters_dirty = true;
+    return st;
+  }
+  for (int i = 0; i < n_scans; ++i)
+    FDEM_CUDA_TRY(cudaEventRecord(m->ev_scan[(ticket0 + i) % kResultRing], s));
+  m->lc.mine += static_cast<int64_t>(BN_COUNT) * n_scans;
+  m->seq = ticket0 + n_scans;
+  mp->last_ticket = ticket0 + n_scans - 1;
+  m->geom_stale = true;
+  mp->last_n = static_cast<uint32_t>(n_points[n_scans - 1]);
+  mp->last_raw = false;
+  mp->last_had_work = true;
+  mp->pending = true;
+  if (!stats) return FDEM_OK;   // queued: fdem_mapper_wait() reads the last scan's statistics
+  FDEM_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < n_scans; ++i) {
+    const ScanResult& r = m->h_result[(ticket0 + i) % kResultRing];
+    stats[i].n_input = static_cast<int64_t>(n_points[i]);
+    stats[i].n_kept = r.counters[CNT_KEPT];
+    stats[i].n_cells = r.counters[CNT_CELLS];
+    stats[i].n_voxels = 0;
+    stats[i].integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
+    stats[i].voxel_box_violations = 0;
+  }
+  return finish_scan(mp, nullptr);
 }
 
 fdem_status fdem_mapper_wait(fdem_mapper* mp, fdem_scan_stats* stats) {

@@ -134,6 +134,12 @@ struct LayerTable {
   int32_t basic[3];  // indices of elevation, elevation_min, elevation_max
 };
 
+// what a deferred commit hands to the back prologue of the same scan (batched integration)
+struct MoveRecord {
+  MoveResult mr;
+  GridGeom g_new;
+};
+
 struct CommitParams {
   double robot_x, robot_y;
   int32_t local_mode;
@@ -141,6 +147,11 @@ struct CommitParams {
   uint32_t invalid_key;
   float* obstacle;
   const uint32_t* touched_keys;
+  // batched integration: the commit only computes the new geometry (so the NEXT scan's K1 can
+  // start) and records the move; every write to map layers waits for back_prologue_kernel,
+  // which runs after the previous scan's estimator
+  int32_t defer;
+  MoveRecord* move_out;
   int32_t tile_path;  // 1: also hand out bucket segments (TileBuffers) and let K3t count cells
   TileBuffers tb;
 };
@@ -157,6 +168,19 @@ struct ScatterParams {
   const DeviceState* st_cur;
   float* obstacle;
   const uint32_t* touched_keys;
+};
+
+// back prologue of a scan in a batch: the map writes the commit / scatter kernels do in the
+// one-scan pipeline (obstacle reset, LOCAL-mode move clearing, touched-count hand-over)
+struct BackParams {
+  const uint32_t* counters;
+  const DeviceState* st_cur;   // state published by the previous scan (touched list length)
+  DeviceState* st_out;         // this scan's state slot
+  const MoveRecord* move;
+  float* obstacle;
+  const uint32_t* touched_keys;
+  uint32_t invalid_key;
+  int32_t clear_policy;
 };
 
 // what K3t's last CTA needs to end the scan (publish); all null/0 when a separate
@@ -208,6 +232,7 @@ struct KernelDesc {
 };
 KernelDesc desc_preprocess_bin(uint32_t n);
 KernelDesc desc_commit();
+KernelDesc desc_back_prologue();
 KernelDesc desc_publish();
 KernelDesc desc_scatter_records(uint32_t n);
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits);

@@ -409,18 +409,56 @@ commit_move_clear_kernel(const __grid_constant__ CommitParams p,
     if (p.local_mode && kept > 0) g_new = geom_move(g_old, p.robot_x, p.robot_y, mr);
     if (blockIdx.x == nA + nB) {
       st_out->geom = g_new;
-      // The touched list is replaced only when this scan produced observations.  Global
-      // sort path: K3 writes one slot per sorted element (invalid_key except at segment
-      // tails).  Tile path: K3t appends compactly and counts up from 0.
-      if (s_inside > 0) st_out->touched_count = p.tile_path ? 0u : s_inside;
-      else st_out->touched_count = st_in->touched_count;
+      if (p.defer) {
+        // batched integration: the map writes (and the touched-count hand-over, which the
+        // previous scan's estimator may still be producing) belong to back_prologue_kernel
+        p.move_out->mr = mr;
+        p.move_out->g_new = g_new;
+      } else {
+        // The touched list is replaced only when this scan produced observations.  Global
+        // sort path: K3 writes one slot per sorted element (invalid_key except at segment
+        // tails).  Tile path: K3t appends compactly and counts up from 0.
+        if (s_inside > 0) st_out->touched_count = p.tile_path ? 0u : s_inside;
+        else st_out->touched_count = st_in->touched_count;
+      }
     }
   }
   __syncthreads();
-  if (mr.clear_all || mr.n_spans > 0) {
+  if (!p.defer && (mr.clear_all || mr.n_spans > 0)) {
     const uint32_t nC = gridDim.x - nA - nB;
     const size_t tid = static_cast<size_t>(blockIdx.x - nA - nB) * blockDim.x + threadIdx.x;
     clear_spans(g_new, mr, lt, p.clear_policy, tid, static_cast<size_t>(nC) * blockDim.x);
+  }
+}
+
+// Batched integration, first kernel of a scan's BACK half (runs after the previous scan's
+// estimator; the front half — K1, commit, scatter — of this scan ran beside it):
+//   * touched-count hand-over: this scan's list starts empty if it has observations
+//   * updateObstacle's map_.clear(obstacle) restricted to the previous touched cells
+//   * GridMap::move()'s clearing of the vacated rows / columns recorded by the commit
+__global__ void __launch_bounds__(kBlock)
+back_prologue_kernel(const __grid_constant__ BackParams p, const __grid_constant__ LayerTable lt) {
+  const uint32_t n_inside = p.counters[CNT_INSIDE];
+  const uint32_t prev = p.st_cur->touched_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.st_out->touched_count = n_inside > 0 ? 0u : prev;
+  const uint32_t nB = gridDim.x / 2;
+  if (blockIdx.x < nB) {
+    if (n_inside > 0 && p.obstacle) {
+      const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+      const size_t nthreads = static_cast<size_t>(nB) * blockDim.x;
+      for (size_t j = tid; j < prev; j += nthreads) {
+        const uint32_t k = p.touched_keys[j];
+        if (k != p.invalid_key) p.obstacle[k] = nan_f32();
+      }
+    }
+    return;
+  }
+  __shared__ MoveRecord rec;
+  if (threadIdx.x == 0) rec = *p.move;
+  __syncthreads();
+  if (rec.mr.clear_all || rec.mr.n_spans > 0) {
+    const size_t tid = static_cast<size_t>(blockIdx.x - nB) * blockDim.x + threadIdx.x;
+    clear_spans(rec.g_new, rec.mr, lt, p.clear_policy, tid, static_cast<size_t>(gridDim.x - nB) * blockDim.x);
   }
 }
 
@@ -627,6 +665,9 @@ KernelDesc desc_preprocess_bin(uint32_t n) {
 KernelDesc desc_commit() {
   return KernelDesc{reinterpret_cast<const void*>(&commit_move_clear_kernel), dim3(148),
                     dim3(kBlock), 0};
+}
+KernelDesc desc_back_prologue() {
+  return KernelDesc{reinterpret_cast<const void*>(&back_prologue_kernel), dim3(148), dim3(kBlock), 0};
 }
 KernelDesc desc_publish() {
   return KernelDesc{reinterpret_cast<const void*>(&publish_kernel), dim3(1), dim3(32), 0};

@@ -205,6 +205,20 @@ fdem_status fdem_mapper_integrate_async(fdem_mapper* m, const float* xyzw, const
                                         const uint8_t* rgb, size_t n,
                                         const double T_base_sensor[16],
                                         const double T_world_base[16]);
+/* n_scans (1..8) consecutive integrate() calls in one go — for callers that have several scans at
+ * hand (bag replay, several sensors per tick).  The result is exactly that of calling
+ * fdem_mapper_integrate n_scans times; what changes is the schedule: the scans go to the device
+ * as ONE graph in which scan k+1's transform / binning / partition kernels run beside scan k's
+ * per-cell estimator (they touch only scan scratch and the chain of window geometries), so a
+ * scan costs max(front, back) instead of front + back.  Arrays of n_scans entries; transforms
+ * are n_scans x 16 doubles; intensity / rgb may be NULL (no such channel) — all scans of a batch
+ * carry the same channels.  Device-resident inputs take the overlapped schedule; host inputs,
+ * raycasting and the global-sort path fall back to scan-after-scan.  stats: n_scans entries, or
+ * NULL to queue the batch without waiting (then see fdem_mapper_wait). */
+fdem_status fdem_mapper_integrate_batch(fdem_mapper* m, int32_t n_scans, const float* const* xyzw,
+                                        const float* const* intensity, const uint8_t* const* rgb,
+                                        const size_t* num_points, const double* T_base_sensor,
+                                        const double* T_world_base, fdem_scan_stats* stats);
 /* blocks until every queued scan is done; *stats (optional) = the LAST scan's stats. */
 fdem_status fdem_mapper_wait(fdem_mapper* m, fdem_scan_stats* stats);
 /* Streaming form of the same call: submit() queues a scan and returns its ticket at once;

@@ -47,3 +47,60 @@ def test_bucket_sizes_give_the_same_map(fdem, monkeypatch, name, n_scans, bucket
     wl = syn.WORKLOADS[name]
     gmap, omap, *_ = run_pair(fdem, wl, n_scans)
     compare_maps(gmap, omap)
+
+
+@pytest.mark.parametrize("name,n_scans,batch", [("tiny", 12, 3), ("c1_vlp16_local", 16, 8), ("c2_lidar64_local", 9, 4),
+                                                ("c3_rgbd_p2", 10, 5)])
+def test_batched_integration_equals_scan_by_scan(fdem, name, n_scans, batch):
+    """fdem_mapper_integrate_batch runs a batch as ONE graph in which scan k+1's front half
+    overlaps scan k's estimator.  Device-resident inputs (the overlapped schedule), LOCAL maps
+    that move every scan, Kalman and P2, intensity and colour channels, batches mixed with
+    single scans: statistics and every layer must equal the oracle's scan-by-scan result."""
+    import torch
+    import oracle_binding as ob
+    wl = syn.WORKLOADS[name]
+    cfg = wl.config()
+    gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
+    gdem = fdem.FastDEM(gmap, cfg)
+    omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    odem = ob.OracleFastDEM(omap, cfg)
+    scans = [syn.make_scan(wl, k) for k in range(n_scans)]
+    dev = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    clouds = [fdem.PointCloud(dev(s["xyzw"]), dev(s["intensity"]), dev(s["rgb"])) for s in scans]
+    ostats = []
+    for s in scans:
+        ok, st, _ = odem.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], s["rgb"])
+        ostats.append(st)
+    k = 0
+    gstats = []
+    while k < n_scans:
+        if k == batch:   # a single scan between two batches: the two schedules share all state
+            gstats.append(gdem.integrate_stats(clouds[k], scans[k]["T_base_sensor"], scans[k]["T_world_base"]))
+            k += 1
+            continue
+        e = min(k + batch, n_scans)
+        gstats += gdem.integrate_batch(clouds[k:e], [(s["T_base_sensor"], s["T_world_base"]) for s in scans[k:e]])
+        k = e
+    assert len(gstats) == n_scans
+    for g, o in zip(gstats, ostats):
+        assert (g.n_kept, g.n_cells, g.integrated) == (o.n_kept, o.n_cells, o.integrated)
+    compare_maps(gmap, omap)
+
+
+def test_batch_with_host_inputs_falls_back(fdem):
+    """Host buffers take the scan-after-scan schedule: same results."""
+    import oracle_binding as ob
+    wl = syn.WORKLOADS["tiny"]
+    gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
+    gdem = fdem.FastDEM(gmap, wl.config())
+    omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    odem = ob.OracleFastDEM(omap, wl.config())
+    scans = [syn.make_scan(wl, k) for k in range(5)]
+    st = gdem.integrate_batch([fdem.PointCloud(s["xyzw"], s["intensity"]) for s in scans],
+                              [(s["T_base_sensor"], s["T_world_base"]) for s in scans])
+    for s in scans:
+        odem.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], None)
+    assert all(x.integrated for x in st)
+    compare_maps(gmap, omap)
+    with pytest.raises(fdem.FdemError):
+        gdem.integrate_batch([fdem.PointCloud(scans[0]["xyzw"])] * 9, [(np.eye(4), np.eye(4))] * 9)
