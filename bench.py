@@ -437,8 +437,8 @@ def main():
         # half overlaps scan k's estimator inside one graph).  Raycasting and the sharded global map
         # keep the scan-by-scan queue.
         S = max(1, min(8, args.batch))
-        if sharded or cfg.raycasting_enabled:
-            S = 1
+        if (sharded and not peer) or cfg.raycasting_enabled:
+            S = 1   # the NCCL transport broadcasts inside every step; raycasting is scan by scan
 
         def submit_many(k0, count):
             kk = k0
