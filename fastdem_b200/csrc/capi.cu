@@ -1075,11 +1075,25 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
     auto edge = [&](cudaGraphNode_t a, cudaGraphNode_t b) -> cudaError_t {
       return cudaGraphAddDependencies(G.graph, &a, &b, 1);
     };
+    // programmatic edges along the back chain (BP_i -> K3_i -> BP_{i+1}): the successor is
+    // launched early and blocks at griddepcontrol.wait, so its launch latency and prologue
+    // hide behind the predecessor (FDEM_BATCH_PDL=1)
+    static const bool pdl = [] { const char* e = std::getenv("FDEM_BATCH_PDL"); return e && e[0] == '1'; }();
+    auto pedge = [&](cudaGraphNode_t a, cudaGraphNode_t b) -> cudaError_t {
+      if (!pdl) return cudaGraphAddDependencies(G.graph, &a, &b, 1);
+      cudaGraphEdgeData ed{};
+      ed.from_port = cudaGraphKernelNodePortProgrammatic;
+      ed.type = cudaGraphDependencyTypeProgrammatic;
+      return cudaGraphAddDependencies_v2(G.graph, &a, &b, &ed, 1);
+    };
     for (int i = 0; i < S; ++i) {
-      for (int k = 1; k < BN_COUNT; ++k) FDEM_CUDA_TRY(edge(G.node[i][k - 1], G.node[i][k]));
+      for (int k = 1; k < BN_COUNT; ++k) {
+        if (k == BN_K3) FDEM_CUDA_TRY(pedge(G.node[i][k - 1], G.node[i][k]));
+        else FDEM_CUDA_TRY(edge(G.node[i][k - 1], G.node[i][k]));
+      }
       if (i + 1 < S) {
         FDEM_CUDA_TRY(edge(G.node[i][BN_K2], G.node[i + 1][BN_K1]));
-        FDEM_CUDA_TRY(edge(G.node[i][BN_K3], G.node[i + 1][BN_BP]));
+        FDEM_CUDA_TRY(pedge(G.node[i][BN_K3], G.node[i + 1][BN_BP]));
       }
       if (i + 2 < S) FDEM_CUDA_TRY(edge(G.node[i][BN_K3], G.node[i + 2][BN_K1]));
     }

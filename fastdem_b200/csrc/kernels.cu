@@ -438,6 +438,8 @@ commit_move_clear_kernel(const __grid_constant__ CommitParams p,
 //   * GridMap::move()'s clearing of the vacated rows / columns recorded by the commit
 __global__ void __launch_bounds__(kBlock)
 back_prologue_kernel(const __grid_constant__ BackParams p, const __grid_constant__ LayerTable lt) {
+  pdl_launch_dependents();  // K3t of this scan may set up (shared-memory init) while this grid runs
+  pdl_wait();               // the previous scan's K3t is complete and flushed from here on
   const uint32_t n_inside = p.counters[CNT_INSIDE];
   const uint32_t prev = p.st_cur->touched_count;
   if (blockIdx.x == 0 && threadIdx.x == 0) p.st_out->touched_count = n_inside > 0 ? 0u : prev;

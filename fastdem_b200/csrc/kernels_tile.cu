@@ -230,6 +230,8 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   bool first_job = true;
   if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x] = globaltimer_ns();
 
+  // batched graphs: the next scan's back prologue may launch now and wait for this grid to finish
+  pdl_launch_dependents();
   // prologue that needs nothing from the scatter kernel: overlaps its tail under PDL
   if (tid == 0) mbar_init(&S.mbar, 1);
   uint32_t phase = 0;
