@@ -8,8 +8,8 @@ configs[1], 64-beam LiDAR 131K pts, 30x30 m @ 0.05 m, Kalman, LOCAL).  One JSON 
 stdout (rank 0).
 
   value    scans/s with the scans already resident in HBM (device pointers through the C-ABI,
-           queued back to back, no host sync inside the timed region), submitted 8 at a time
-           through fdem_mapper_integrate_batch — identical results to 8 integrate() calls, with
+           queued back to back, no host sync inside the timed region), submitted 16 at a time
+           through fdem_mapper_integrate_batch — identical results to 16 integrate() calls, with
            scan k+1's front half overlapping scan k's estimator (--batch 1: one call per scan;
            the JSON also carries that figure as value_scan_by_scan).  The timed steps cycle
            through distinct device-resident scans totalling more than L2 (--l2 flush: a 256 MiB
@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="c5_global at N>1: how the stripes get the scan — 'peer': every rank's K1 reads it in "
                          "place from the ingest rank's HBM over NVLink (CUDA IPC); 'nccl': dist.broadcast")
-    ap.add_argument("--batch", type=int, default=8,
+    ap.add_argument("--batch", type=int, default=16,
                     help="scans per fdem_mapper_integrate_batch call in the device-resident `value` loop "
                          "(1 = one fdem_mapper_integrate_async per scan)")
     ap.add_argument("--no-frame", action="store_true", help="skip the whole-frame (mapping + post-process) block")
@@ -436,7 +436,7 @@ def main():
         # fdem_mapper_integrate_batch call (same results as S integrate() calls; scan k+1's front
         # half overlaps scan k's estimator inside one graph).  Raycasting and the sharded global map
         # keep the scan-by-scan queue.
-        S = max(1, min(8, args.batch))
+        S = max(1, min(16, args.batch))
         if (sharded and not peer) or cfg.raycasting_enabled:
             S = 1   # the NCCL transport broadcasts inside every step; raycasting is scan by scan
 

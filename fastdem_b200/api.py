@@ -672,7 +672,7 @@ class FastDEM:
         self._keep = keep
 
     def integrate_batch(self, clouds, poses, wait: bool = True):
-        """Up to 8 consecutive integrate() calls as one graph in which scan k+1's front half runs
+        """Up to 16 consecutive integrate() calls as one graph in which scan k+1's front half runs
         beside scan k's estimator (fdem_mapper_integrate_batch).  clouds: list of PointCloud;
         poses: list of (T_base_sensor, T_world_base).  Returns the per-scan stats (wait=True) or
         None (queued; see wait())."""

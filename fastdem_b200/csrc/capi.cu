@@ -185,6 +185,7 @@ struct fdem_mapper {
   uint32_t* d_counters2 = nullptr;
   TileBuffers tb2{};
   size_t cap2 = 0;
+  uint32_t* d_batch_counters = nullptr;  // [16][CNT_COUNT]: one counter block per scan of a batch
   DeviceState* d_ring = nullptr;   // [kMaxBatch + 1]
   MoveRecord* d_move = nullptr;    // [2]
   struct BatchGraphState* bg = nullptr;   // [2]: executable graphs used alternately, so one can be
@@ -935,7 +936,7 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
 //   K2_i -> K1_{i+1}                           (geometry after scan i's move)
 //   K3_i -> BP_{i+1}                           (map layers, touched list)
 //   K3_i -> K1_{i+2}                           (scratch set i & 1 is free again)
-constexpr int kMaxBatch = 8;   // = kResultRing: every scan of a batch has its own result slot
+constexpr int kMaxBatch = 16;  // scans per batch graph
 enum { BN_K1 = 0, BN_K2, BN_SC, BN_BP, BN_K3, BN_COUNT };
 
 struct BatchScan {
@@ -950,6 +951,7 @@ struct BatchGraphState {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaGraphNode_t node[kMaxBatch][BN_COUNT] = {};
+  cudaGraphNode_t zero = nullptr;   // head of the graph: all counter blocks -> 0
   int S = 0;
   uint32_t tile_shape_key = 0;  // bucket bits the graph was built for
   BatchScan scan[kMaxBatch];    // this batch's kernel arguments
@@ -977,6 +979,8 @@ fdem_status ensure_batch_scratch(fdem_mapper* mp) {
     FDEM_CUDA_TRY(cudaMemset(mp->d_move, 0, 2 * sizeof(MoveRecord)));
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_counters2, CNT_COUNT * sizeof(uint32_t)));
     FDEM_CUDA_TRY(cudaMemset(mp->d_counters2, 0, CNT_COUNT * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_batch_counters, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMemset(mp->d_batch_counters, 0, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_count, nb));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_offset, nb));
@@ -1011,7 +1015,9 @@ void retarget_for_batch(fdem_mapper* mp, int i, BatchScan& b) {
   tb.bucket_bits = mp->tb.bucket_bits;
   float4* pm = q ? mp->d_pm2 : mp->d_pm;
   uint32_t* keys = q ? mp->d_keys2 : mp->d_keys;
-  uint32_t* counters = q ? mp->d_counters2 : mp->d_counters;
+  // one counter block per scan of the batch, all zeroed by ONE memset node at the head of the
+  // graph: no scan has to re-arm its counters, so only the last scan needs the last-CTA ticket
+  uint32_t* counters = mp->d_batch_counters + static_cast<size_t>(i) * CNT_COUNT;
   const DeviceState* st_in = i == 0 ? m->d_state : mp->d_ring + i;
   DeviceState* st_out = mp->d_ring + i + 1;
   L.pp.bucket_count = tb.bucket_count;
@@ -1026,11 +1032,10 @@ void retarget_for_batch(fdem_mapper* mp, int i, BatchScan& b) {
   L.sp.obstacle = nullptr;     // the back prologue resets the obstacle cells
   L.ep.pm = pm;
   L.tb = tb;
-  L.pub.enabled = 1;
-  L.pub.st_cur = m->d_state;   // publish keeps the map's current state up to date per scan
+  L.pub.st_cur = m->d_state;   // the batch's last scan commits the state and reports to the host
   b.bp = BackParams{};
   b.bp.counters = counters;
-  b.bp.st_cur = m->d_state;
+  b.bp.st_cur = st_in;         // the previous scan's slot: its estimator left the touched count there
   b.bp.st_out = st_out;
   b.bp.move = mp->d_move + q;
   b.bp.obstacle = L.ep.L.obstacle;
@@ -1064,6 +1069,15 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
     if (G.graph) cudaGraphDestroy(G.graph);
     G.exec = nullptr; G.graph = nullptr;
     FDEM_CUDA_TRY(cudaGraphCreate(&G.graph, 0));
+    {
+      cudaMemsetParams zp{};
+      zp.dst = mp->d_batch_counters;
+      zp.value = 0;
+      zp.elementSize = 4;
+      zp.width = static_cast<size_t>(kMaxBatch) * CNT_COUNT;
+      zp.height = 1;
+      FDEM_CUDA_TRY(cudaGraphAddMemsetNode(&G.zero, G.graph, nullptr, 0, &zp));
+    }
     for (int i = 0; i < S; ++i) {
       NodeArgs na[BN_COUNT];
       batch_node_args(G.scan[i], na);
@@ -1072,6 +1086,7 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
         FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i][k], G.graph, nullptr, 0, &kp));
       }
     }
+    FDEM_CUDA_TRY(cudaGraphAddDependencies(G.graph, &G.zero, &G.node[0][BN_K1], 1));
     auto edge = [&](cudaGraphNode_t a, cudaGraphNode_t b) -> cudaError_t {
       return cudaGraphAddDependencies(G.graph, &a, &b, 1);
     };
@@ -1643,6 +1658,7 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   cudaFree(mp->tb2.bucket_list);
   cudaFree(mp->d_ring);
   cudaFree(mp->d_move);
+  cudaFree(mp->d_batch_counters);
   for (cudaEvent_t e : mp->ev_copied)
     if (e) cudaEventDestroy(e);
   if (mp->copy_stream) cudaStreamDestroy(mp->copy_stream);
@@ -1833,7 +1849,7 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
                                         const size_t* n_points, const double* Tbs, const double* Twb,
                                         fdem_scan_stats* stats) {
   FDEM_REQUIRE(mp && xyzw && n_points && Tbs && Twb, "null argument");
-  FDEM_REQUIRE(n_scans >= 1 && n_scans <= kMaxBatch, "a batch holds 1 to 8 scans");
+  FDEM_REQUIRE(n_scans >= 1 && n_scans <= kMaxBatch, "a batch holds 1 to 16 scans");
   fdem_map* m = mp->map;
   DeviceGuard dg(m->device);
   const bool overlapped = mp->use_tile && mp->use_graph && !mp->stage_timing && !mp->cfg.raycasting_enabled;
@@ -1881,6 +1897,7 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
     FDEM_TRY(enqueue_scan(mp, in, &b.L, ticket0 + i));
     b.n = static_cast<uint32_t>(n_points[i]);
     retarget_for_batch(mp, i, b);
+    b.L.pub.enabled = i == n_scans - 1 ? 1 : 0;
   }
   fdem_status st = launch_batch_graph(mp, n_scans, s);
   if (st != FDEM_OK) {
@@ -1899,14 +1916,20 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
   mp->last_had_work = true;
   mp->pending = true;
   if (!stats) return FDEM_OK;   // queued: fdem_mapper_wait() reads the last scan's statistics
+  // per-scan statistics: the counter blocks of the batch, one copy (the last scan's block was
+  // re-armed by its publish; its numbers are in the result slot)
+  uint32_t hc[kMaxBatch][CNT_COUNT];
+  FDEM_CUDA_TRY(cudaMemcpyAsync(hc, mp->d_batch_counters, sizeof(uint32_t) * CNT_COUNT * n_scans,
+                                cudaMemcpyDeviceToHost, s));
   FDEM_CUDA_TRY(cudaStreamSynchronize(s));
+  const ScanResult& last = m->h_result[(ticket0 + n_scans - 1) % kResultRing];
   for (int i = 0; i < n_scans; ++i) {
-    const ScanResult& r = m->h_result[(ticket0 + i) % kResultRing];
+    const uint32_t* c = i == n_scans - 1 ? last.counters : hc[i];
     stats[i].n_input = static_cast<int64_t>(n_points[i]);
-    stats[i].n_kept = r.counters[CNT_KEPT];
-    stats[i].n_cells = r.counters[CNT_CELLS];
+    stats[i].n_kept = c[CNT_KEPT];
+    stats[i].n_cells = c[CNT_CELLS];
     stats[i].n_voxels = 0;
-    stats[i].integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
+    stats[i].integrated = c[CNT_KEPT] > 0 ? 1 : 0;
     stats[i].voxel_box_violations = 0;
   }
   return finish_scan(mp, nullptr);

@@ -205,7 +205,7 @@ fdem_status fdem_mapper_integrate_async(fdem_mapper* m, const float* xyzw, const
                                         const uint8_t* rgb, size_t n,
                                         const double T_base_sensor[16],
                                         const double T_world_base[16]);
-/* n_scans (1..8) consecutive integrate() calls in one go — for callers that have several scans at
+/* n_scans (1..16) consecutive integrate() calls in one go — for callers that have several scans at
  * hand (bag replay, several sensors per tick).  The result is exactly that of calling
  * fdem_mapper_integrate n_scans times; what changes is the schedule: the scans go to the device
  * as ONE graph in which scan k+1's transform / binning / partition kernels run beside scan k's

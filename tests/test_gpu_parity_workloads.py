@@ -49,7 +49,7 @@ def test_bucket_sizes_give_the_same_map(fdem, monkeypatch, name, n_scans, bucket
     compare_maps(gmap, omap)
 
 
-@pytest.mark.parametrize("name,n_scans,batch", [("tiny", 12, 3), ("c1_vlp16_local", 16, 8), ("c2_lidar64_local", 9, 4),
+@pytest.mark.parametrize("name,n_scans,batch", [("tiny", 12, 3), ("tiny", 40, 16), ("c1_vlp16_local", 16, 8), ("c2_lidar64_local", 9, 4),
                                                 ("c3_rgbd_p2", 10, 5)])
 def test_batched_integration_equals_scan_by_scan(fdem, name, n_scans, batch):
     """fdem_mapper_integrate_batch runs a batch as ONE graph in which scan k+1's front half
@@ -103,4 +103,4 @@ def test_batch_with_host_inputs_falls_back(fdem):
     assert all(x.integrated for x in st)
     compare_maps(gmap, omap)
     with pytest.raises(fdem.FdemError):
-        gdem.integrate_batch([fdem.PointCloud(scans[0]["xyzw"])] * 9, [(np.eye(4), np.eye(4))] * 9)
+        gdem.integrate_batch([fdem.PointCloud(scans[0]["xyzw"])] * 17, [(np.eye(4), np.eye(4))] * 17)
