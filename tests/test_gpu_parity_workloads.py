@@ -104,3 +104,35 @@ def test_batch_with_host_inputs_falls_back(fdem):
     compare_maps(gmap, omap)
     with pytest.raises(fdem.FdemError):
         gdem.integrate_batch([fdem.PointCloud(scans[0]["xyzw"])] * 17, [(np.eye(4), np.eye(4))] * 17)
+
+
+def test_batch_with_jumps_empty_and_filtered_scans(fdem):
+    """Inside one batch: a 100 m jump (the whole LOCAL window is vacated: clear_all), a scan whose
+    points are all filtered (no move, nothing touched), a scan that lands outside the window's
+    previous position — the deferred commit / back prologue must treat them like the per-scan
+    pipeline does."""
+    import torch
+    import oracle_binding as ob
+    wl = syn.WORKLOADS["tiny"]
+    cfg = wl.config()
+    gmap = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
+    gdem = fdem.FastDEM(gmap, cfg)
+    omap = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    odem = ob.OracleFastDEM(omap, cfg)
+    scans = [syn.make_scan(wl, k) for k in range(10)]
+    for k, s in enumerate(scans):
+        s["T_world_base"] = np.array(s["T_world_base"], dtype=np.float64).copy()
+        if k >= 4:
+            s["T_world_base"][0, 3] += 100.0       # scans 4.. happen 100 m away
+        if k == 6:
+            s["xyzw"] = s["xyzw"].copy()
+            s["xyzw"][:, :3] *= 1000.0             # every point beyond range_max: filtered, no move
+        if k == 8:
+            s["T_world_base"][1, 3] -= 3.05        # a sideways hop of 30 cells and a half
+    clouds = [fdem.PointCloud(torch.from_numpy(s["xyzw"]).cuda(), torch.from_numpy(s["intensity"]).cuda()) for s in scans]
+    gst = gdem.integrate_batch(clouds, [(s["T_base_sensor"], s["T_world_base"]) for s in scans])
+    for s, g in zip(scans, gst):
+        ok, o, _ = odem.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], None)
+        assert (g.integrated, g.n_kept, g.n_cells) == (int(ok), o.n_kept, o.n_cells)
+    assert gst[6].integrated == 0 and gst[6].n_cells == 0
+    compare_maps(gmap, omap)
