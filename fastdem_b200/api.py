@@ -710,6 +710,12 @@ class FastDEM:
             return None
         return [FdemScanStats.from_buffer_copy(st) for st in stats]
 
+    def last_batch_stats(self, n_scans: int):
+        """Per-scan stats of the most recent integrate_batch(..., wait=False) (waits for it)."""
+        arr = (FdemScanStats * n_scans)()
+        check(self._lib.fdem_mapper_last_batch_stats(self._h, arr, n_scans))
+        return [FdemScanStats.from_buffer_copy(st) for st in arr]
+
     def submit(self, cloud: PointCloud, T_base_sensor, T_world_base) -> int:
         """Queue one scan; returns its ticket.  `submit(k+1); collect(k)` overlaps the
         host->device copy of scan k+1 with the kernels of scan k."""

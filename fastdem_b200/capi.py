@@ -118,6 +118,7 @@ SIGNATURES = {
     "fdem_mapper_wait": (_ST, [_P, C.POINTER(FdemScanStats)]),
     "fdem_mapper_integrate_batch": (_ST, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "fdem_mapper_last_batch_stats": (_ST, [_P, C.c_void_p, C.c_int32]),
     "fdem_mapper_submit": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p, C.POINTER(C.c_uint64)]),
     "fdem_mapper_collect": (_ST, [_P, C.c_uint64, C.POINTER(FdemScanStats)]),
     "fdem_mapper_update": (_ST, [_P, _f32p, _f32p, _f32p, _u8p, C.c_size_t, C.c_double, C.c_double,

@@ -182,10 +182,13 @@ struct fdem_mapper {
   // front half can run beside scan k's estimator, a ring of state slots, the batch graph
   float4* d_pm2 = nullptr;
   uint32_t* d_keys2 = nullptr;
-  uint32_t* d_counters2 = nullptr;
   TileBuffers tb2{};
   size_t cap2 = 0;
   uint32_t* d_batch_counters = nullptr;  // [16][CNT_COUNT]: one counter block per scan of a batch
+  uint32_t* h_batch_counters = nullptr;  // pinned copy, written by a memcpy node at the end of every batch
+  int last_batch_n = 0;                  // scans in the most recent batch (fdem_mapper_last_batch_stats)
+  uint64_t last_batch_ticket0 = 0;
+  size_t last_batch_points[16] = {};
   DeviceState* d_ring = nullptr;   // [kMaxBatch + 1]
   MoveRecord* d_move = nullptr;    // [2]
   struct BatchGraphState* bg = nullptr;   // [2]: executable graphs used alternately, so one can be
@@ -952,6 +955,7 @@ struct BatchGraphState {
   cudaGraphExec_t exec = nullptr;
   cudaGraphNode_t node[kMaxBatch][BN_COUNT] = {};
   cudaGraphNode_t zero = nullptr;   // head of the graph: all counter blocks -> 0
+  cudaGraphNode_t report = nullptr; // counter blocks of scans 0..S-2 -> pinned host memory
   int S = 0;
   uint32_t tile_shape_key = 0;  // bucket bits the graph was built for
   BatchScan scan[kMaxBatch];    // this batch's kernel arguments
@@ -977,8 +981,8 @@ fdem_status ensure_batch_scratch(fdem_mapper* mp) {
     FDEM_CUDA_TRY(cudaMemset(mp->d_ring, 0, (kMaxBatch + 1) * sizeof(DeviceState)));
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_move, 2 * sizeof(MoveRecord)));
     FDEM_CUDA_TRY(cudaMemset(mp->d_move, 0, 2 * sizeof(MoveRecord)));
-    FDEM_CUDA_TRY(cudaMalloc(&mp->d_counters2, CNT_COUNT * sizeof(uint32_t)));
-    FDEM_CUDA_TRY(cudaMemset(mp->d_counters2, 0, CNT_COUNT * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaHostAlloc(&mp->h_batch_counters, kMaxBatch * CNT_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
+    std::memset(mp->h_batch_counters, 0, kMaxBatch * CNT_COUNT * sizeof(uint32_t));
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_batch_counters, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     FDEM_CUDA_TRY(cudaMemset(mp->d_batch_counters, 0, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
@@ -1111,6 +1115,14 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
         FDEM_CUDA_TRY(pedge(G.node[i][BN_K3], G.node[i + 1][BN_BP]));
       }
       if (i + 2 < S) FDEM_CUDA_TRY(edge(G.node[i][BN_K3], G.node[i + 2][BN_K1]));
+    }
+    if (S > 1) {
+      // every scan's statistics reach the host, like in the per-scan pipeline: the last scan's
+      // through its publish, the others' through one copy of their counter blocks, issued as
+      // soon as the second-to-last scan is done (beside the last scan, off the critical path)
+      FDEM_CUDA_TRY(cudaGraphAddMemcpyNode1D(&G.report, G.graph, &G.node[S - 2][BN_K3], 1, mp->h_batch_counters,
+                                             mp->d_batch_counters, sizeof(uint32_t) * CNT_COUNT * (S - 1),
+                                             cudaMemcpyDeviceToHost));
     }
     FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
     G.S = S;
@@ -1650,7 +1662,6 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   destroy_batch_graph(mp);
   cudaFree(mp->d_pm2);
   cudaFree(mp->d_keys2);
-  cudaFree(mp->d_counters2);
   cudaFree(mp->tb2.records);
   cudaFree(mp->tb2.bucket_count);
   cudaFree(mp->tb2.bucket_offset);
@@ -1659,6 +1670,7 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   cudaFree(mp->d_ring);
   cudaFree(mp->d_move);
   cudaFree(mp->d_batch_counters);
+  cudaFreeHost(mp->h_batch_counters);
   for (cudaEvent_t e : mp->ev_copied)
     if (e) cudaEventDestroy(e);
   if (mp->copy_stream) cudaStreamDestroy(mp->copy_stream);
@@ -1874,6 +1886,12 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
   for (int i = 0; i < n_scans; ++i) n_max = std::max(n_max, n_points[i]);
   FDEM_TRY(ensure_capacity(mp, n_max));
   FDEM_TRY(ensure_batch_scratch(mp));
+  if (mp->tile_dirty) {
+    // after a failed scan the bucket scratch may hold leftovers: the primary set is re-zeroed by
+    // the scan builder below, the second set here
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb2.bucket_count, 0, mp->max_buckets * sizeof(uint32_t), s));
+    FDEM_CUDA_TRY(cudaMemsetAsync(mp->tb2.bucket_cursor, 0, mp->max_buckets * sizeof(uint32_t), s));
+  }
   if (!mp->bg) mp->bg = new (std::nothrow) BatchGraphState[2]();
   mp->bg_flip ^= 1;
   if (!mp->bg) return set_error(FDEM_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -1915,24 +1933,33 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
   mp->last_raw = false;
   mp->last_had_work = true;
   mp->pending = true;
-  if (!stats) return FDEM_OK;   // queued: fdem_mapper_wait() reads the last scan's statistics
-  // per-scan statistics: the counter blocks of the batch, one copy (the last scan's block was
-  // re-armed by its publish; its numbers are in the result slot)
-  uint32_t hc[kMaxBatch][CNT_COUNT];
-  FDEM_CUDA_TRY(cudaMemcpyAsync(hc, mp->d_batch_counters, sizeof(uint32_t) * CNT_COUNT * n_scans,
-                                cudaMemcpyDeviceToHost, s));
+  mp->last_batch_n = n_scans;
+  mp->last_batch_ticket0 = ticket0;
+  for (int i = 0; i < n_scans; ++i) mp->last_batch_points[i] = n_points[i];
+  if (!stats) return FDEM_OK;   // queued: fdem_mapper_wait(), then fdem_mapper_last_batch_stats()
   FDEM_CUDA_TRY(cudaStreamSynchronize(s));
-  const ScanResult& last = m->h_result[(ticket0 + n_scans - 1) % kResultRing];
+  FDEM_TRY(fdem_mapper_last_batch_stats(mp, stats, n_scans));
+  return finish_scan(mp, nullptr);
+}
+
+fdem_status fdem_mapper_last_batch_stats(fdem_mapper* mp, fdem_scan_stats* stats, int32_t n_scans) {
+  FDEM_REQUIRE(mp && stats, "null argument");
+  FDEM_REQUIRE(n_scans == mp->last_batch_n && n_scans > 0, "n_scans must equal the size of the last batch");
+  fdem_map* m = mp->map;
+  DeviceGuard dg(m->device);
+  FDEM_REQUIRE(mp->last_batch_ticket0 + n_scans == m->seq, "other scans were integrated after the batch");
+  FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  const ScanResult& last = m->h_result[(mp->last_batch_ticket0 + n_scans - 1) % kResultRing];
   for (int i = 0; i < n_scans; ++i) {
-    const uint32_t* c = i == n_scans - 1 ? last.counters : hc[i];
-    stats[i].n_input = static_cast<int64_t>(n_points[i]);
+    const uint32_t* c = i == n_scans - 1 ? last.counters : mp->h_batch_counters + static_cast<size_t>(i) * CNT_COUNT;
+    stats[i].n_input = static_cast<int64_t>(mp->last_batch_points[i]);
     stats[i].n_kept = c[CNT_KEPT];
     stats[i].n_cells = c[CNT_CELLS];
     stats[i].n_voxels = 0;
     stats[i].integrated = c[CNT_KEPT] > 0 ? 1 : 0;
     stats[i].voxel_box_violations = 0;
   }
-  return finish_scan(mp, nullptr);
+  return FDEM_OK;
 }
 
 fdem_status fdem_mapper_wait(fdem_mapper* mp, fdem_scan_stats* stats) {

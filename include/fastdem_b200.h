@@ -219,6 +219,10 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* m, int32_t n_scans, const f
                                         const float* const* intensity, const uint8_t* const* rgb,
                                         const size_t* num_points, const double* T_base_sensor,
                                         const double* T_world_base, fdem_scan_stats* stats);
+/* per-scan statistics of the most recent batch (waits for it): what a queued batch
+ * (stats == NULL) would have returned.  Every scan's counters reach pinned host memory at the end
+ * of the batch, as they do scan by scan. */
+fdem_status fdem_mapper_last_batch_stats(fdem_mapper* m, fdem_scan_stats* stats, int32_t n_scans);
 /* blocks until every queued scan is done; *stats (optional) = the LAST scan's stats. */
 fdem_status fdem_mapper_wait(fdem_mapper* m, fdem_scan_stats* stats);
 /* Streaming form of the same call: submit() queues a scan and returns its ticket at once;

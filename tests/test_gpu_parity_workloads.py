@@ -79,7 +79,12 @@ def test_batched_integration_equals_scan_by_scan(fdem, name, n_scans, batch):
             k += 1
             continue
         e = min(k + batch, n_scans)
-        gstats += gdem.integrate_batch(clouds[k:e], [(s["T_base_sensor"], s["T_world_base"]) for s in scans[k:e]])
+        poses = [(s["T_base_sensor"], s["T_world_base"]) for s in scans[k:e]]
+        if (k // batch) % 2:   # queued batch: the per-scan statistics are fetched afterwards
+            assert gdem.integrate_batch(clouds[k:e], poses, wait=False) is None
+            gstats += gdem.last_batch_stats(e - k)
+        else:
+            gstats += gdem.integrate_batch(clouds[k:e], poses)
         k = e
     assert len(gstats) == n_scans
     for g, o in zip(gstats, ostats):
