@@ -187,7 +187,7 @@ def run_reference(args, wl, rank, world):
         odem.integrate(s["xyzw"], *pose_for(wl, k), s["intensity"], s["rgb"])
         k += 1
     total = 0.0
-    budget_s = 120.0
+    budget_s = 60.0
     done = 0
     for _ in range(args.steps):
         s = ring[k % len(ring)]
@@ -293,7 +293,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_lidar64_local")
