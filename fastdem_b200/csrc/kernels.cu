@@ -15,6 +15,7 @@
 // indices are bit-identical and heights/variances agree to the last bit in practice.
 // Reference file:line citations are relative to /root/reference/.
 #include <float.h>
+#include <cstdlib>
 #include <math.h>
 
 #include "device_types.h"
@@ -669,7 +670,14 @@ KernelDesc desc_commit() {
                     dim3(kBlock), 0};
 }
 KernelDesc desc_back_prologue() {
-  return KernelDesc{reinterpret_cast<const void*>(&back_prologue_kernel), dim3(148), dim3(kBlock), 0};
+  // a small grid: the kernel sits on the batch's serial back chain and its work is tens of
+  // thousands of independent stores at most (FDEM_BP_CTAS overrides, for tuning)
+  static const int ctas = [] {
+    const char* e = std::getenv("FDEM_BP_CTAS");
+    const int v = e ? std::atoi(e) : 148;
+    return v >= 2 && v <= 1184 ? v : 148;
+  }();
+  return KernelDesc{reinterpret_cast<const void*>(&back_prologue_kernel), dim3(ctas), dim3(kBlock), 0};
 }
 KernelDesc desc_publish() {
   return KernelDesc{reinterpret_cast<const void*>(&publish_kernel), dim3(1), dim3(32), 0};
