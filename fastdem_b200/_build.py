@@ -27,6 +27,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("FDEM_PROBES") == "1":   # tuning probes in K3t (tools/phase_probe.py); never in the product build
+    NVCC_FLAGS.append("-DFDEM_PROBES")
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

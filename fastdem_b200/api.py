@@ -293,6 +293,11 @@ class ElevationMap:
     # ── lifetime ──
     def setGeometry(self, width: float, height: float, resolution: float,
                     row_stripe: Optional[Sequence[int]] = None) -> None:
+        if self._h and row_stripe is None:
+            # in place, like nanoGrid setGeometry + clearAll (elevation_map.hpp:112-116): the handle
+            # and every FastDEM bound to it stay valid (io.loadNpz restores into a live map)
+            check(self._lib.fdem_map_set_geometry(self._h, width, height, resolution))
+            return
         if self._h:
             check(self._lib.fdem_map_destroy(self._h))
             self._h = C.c_void_p()
@@ -777,15 +782,19 @@ class FastDEM:
         check(self._lib.fdem_mapper_last_rasterized(self._h, xyz.ctypes.data, C.byref(nc)))
         return PointCloud(xyz[:nc.value], frame_id=self._map.getFrameId())
 
+    # tuning probes: only a -DFDEM_PROBES build exports these (tools/phase_probe.py)
     def debug_cta_times(self):
+        fn = self._lib.fdem_mapper_debug_cta_times  # AttributeError: production build
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]
         out = (C.c_uint64 * 1024)()
-        check(self._lib.fdem_mapper_debug_cta_times(self._h, out))
-        a = np.array(out, dtype=np.uint64).reshape(512, 2)
-        return a
+        check(fn(self._h, out))
+        return np.array(out, dtype=np.uint64).reshape(512, 2)
 
     def debug_phase_clocks(self):
+        fn = self._lib.fdem_mapper_debug_phase_clocks
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]
         out = (C.c_int64 * 16)()
-        check(self._lib.fdem_mapper_debug_phase_clocks(self._h, out))
+        check(fn(self._h, out))
         return list(out)
 
     def set_cell_sort(self, mode: int) -> None:

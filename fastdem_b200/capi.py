@@ -80,6 +80,8 @@ SIGNATURES = {
     "fdem_map_create": (_ST, [C.c_float, C.c_float, C.c_float, C.c_int32, _P, C.POINTER(_P)]),
     "fdem_map_create_stripe": (_ST, [C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32,
                                      C.c_int32, _P, C.POINTER(_P)]),
+    "fdem_map_set_geometry": (_ST, [_P, C.c_float, C.c_float, C.c_float]),
+    "fdem_config_validate": (_ST, [C.POINTER(FdemConfig), C.POINTER(C.c_int32)]),
     "fdem_map_destroy": (_ST, [_P]),
     "fdem_map_get_geometry": (_ST, [_P, C.POINTER(FdemGeometry)]),
     "fdem_map_set_position": (_ST, [_P, C.c_double, C.c_double]),
@@ -140,14 +142,18 @@ SIGNATURES = {
     "fdem_ipc_export": (_ST, [C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(FdemIpcHandle)]),
     "fdem_ipc_import": (_ST, [C.c_int32, C.POINTER(FdemIpcHandle), C.POINTER(C.c_void_p)]),
     "fdem_ipc_close": (_ST, [C.c_int32, C.c_void_p]),
+    "fdem_shard_create": (_ST, [_P, C.c_int32, C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fdem_shard_destroy": (_ST, [_P]),
+    "fdem_shard_export": (_ST, [_P, C.POINTER(FdemIpcHandle)]),
+    "fdem_shard_connect": (_ST, [_P, C.c_void_p]),
+    "fdem_shard_integrate": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p]),
+    "fdem_shard_wait": (_ST, [_P, C.POINTER(FdemScanStats)]),
     "fdem_uncertainty_fusion": (_ST, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "fdem_feature_extraction": (_ST, [_P, C.c_float, C.c_int32, C.c_float, C.c_float]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),
     "fdem_mapper_set_cell_sort": (_ST, [_P, C.c_int32]),
-    "fdem_mapper_debug_phase_clocks": (_ST, [_P, C.POINTER(C.c_int64)]),
-    "fdem_mapper_debug_cta_times": (_ST, [_P, C.POINTER(C.c_uint64)]),
     "fdem_mapper_stage_times": (_ST, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

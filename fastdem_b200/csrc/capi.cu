@@ -48,6 +48,13 @@ static fdem_status set_error(fdem_status s, const std::string& msg) {
     if (_s != FDEM_OK) return _s;         \
   } while (0)
 
+// a FastDEM whose map was destroyed under it (fdem_map_destroy detaches it)
+#define FDEM_MAPPER_ALIVE(mp)                                                               \
+  do {                                                                                      \
+    if ((mp) && !(mp)->map)                                                                 \
+      return set_error(FDEM_ERR_INVALID_ARGUMENT, "the mapper's map has been destroyed");   \
+  } while (0)
+
 #define FDEM_REQUIRE(cond, msg) \
   do {                          \
     if (!(cond)) return set_error(FDEM_ERR_INVALID_ARGUMENT, msg); \
@@ -62,6 +69,11 @@ constexpr float kNaN = std::numeric_limits<float>::quiet_NaN();
 struct Layer {
   std::string name;
   float* d = nullptr;
+  // Layers the reference creates lazily on a condition only the device learns (first scan WITH
+  // observations that carries the channel; first applyRaycasting that passes its guards) are
+  // allocated when first needed but stay invisible to the map API until the device has reported
+  // the StateFlag that reveals them — exists() / getLayers() then match the reference's.
+  uint32_t hidden_until = 0;  // 0 = visible
 };
 
 // what the last kernel of a scan leaves for the host (copied D2H into pinned memory)
@@ -88,7 +100,10 @@ struct fdem_map {
   uint32_t* d_touched_keys = nullptr;
   float* d_touched_minz = nullptr;
   size_t touched_cap = 0;
-  bool obstacle_full_clear = false;  // obstacle was written behind the mapper's back
+  bool obstacle_full_clear = false;  // obstacle was written behind the mapper's back: the next
+                                     // scan sets SF_OBSTACLE_DIRTY on the device first
+  uint32_t state_flags = 0;          // host mirror of DeviceState::flags (valid when !geom_stale)
+  std::vector<fdem_mapper*> mappers; // FastDEM objects bound to this map (they hold map-sized scratch)
   // raycasting scratch (allocated on first use)
   uint32_t* d_ray_min_enc = nullptr;
   uint32_t* d_hits = nullptr;
@@ -142,7 +157,8 @@ struct ScanGraph {
 }  // namespace
 
 struct fdem_mapper {
-  fdem_map* map = nullptr;
+  fdem_map* map = nullptr;   // null once the map has been destroyed under the mapper
+  int device = 0;
   fdem_config cfg{};
   size_t cap = 0;  // scratch capacity in points
   // host-input staging, double buffered: slot q % kStageRing of scan q
@@ -157,8 +173,14 @@ struct fdem_mapper {
   uint64_t last_ticket = 0;
   float4* d_pm = nullptr;
   uint32_t *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr, *d_svals = nullptr;
-  uint64_t *d_vkeys = nullptr, *d_svkeys = nullptr;  // voxel keys (raycasting)
-  uint32_t* d_sel = nullptr;                         // voxel representatives
+  uint64_t *d_vkeys = nullptr, *d_svkeys = nullptr;  // 63-bit voxel keys (raycasting, unbounded range)
+  // raycasting branch (runs beside scatter + K3t on aux_stream): its own key / value buffers
+  uint32_t *d_vk32 = nullptr, *d_svk32 = nullptr, *d_vv = nullptr, *d_svv = nullptr;
+  float4* d_rays = nullptr;                          // rays to trace (end points), (length, azimuth) bundles
+  float4* d_rays_tmp = nullptr;                      // the same in discovery order
+  uint32_t* d_ray_hist = nullptr;                    // counting-sort histogram + cursors
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_geom = nullptr, ev_rays = nullptr;
   void* d_sort_temp = nullptr;
   size_t sort_temp_bytes = 0;
   uint32_t* d_counters = nullptr;
@@ -226,6 +248,12 @@ Layer* find_layer(fdem_map* m, const char* name) {
   return nullptr;
 }
 
+void apply_state_flags(fdem_map* m, uint32_t flags) {
+  m->state_flags = flags;
+  for (auto& l : m->layers)
+    if (l.hidden_until & flags) l.hidden_until = 0;
+}
+
 float* layer_ptr(fdem_map* m, const char* name) {
   Layer* l = find_layer(m, name);
   return l ? l->d : nullptr;
@@ -262,8 +290,19 @@ fdem_status add_layer(fdem_map* m, const char* name, float fill) {
 }
 
 fdem_status ensure_layer(fdem_map* m, const char* name, float fill) {
-  if (find_layer(m, name)) return FDEM_OK;
+  if (Layer* l = find_layer(m, name)) {
+    l->hidden_until = 0;
+    return FDEM_OK;
+  }
   return add_layer(m, name, fill);
+}
+
+// storage for a lazily created layer: invisible until the device reports `flag`
+fdem_status ensure_hidden_layer(fdem_map* m, const char* name, float fill, uint32_t flag) {
+  if (find_layer(m, name)) return FDEM_OK;
+  FDEM_TRY(add_layer(m, name, fill));
+  if (!(m->state_flags & flag)) m->layers.back().hidden_until = flag;
+  return FDEM_OK;
 }
 
 // bring the host mirror of the geometry up to date with the device
@@ -274,13 +313,28 @@ fdem_status refresh_geometry(fdem_map* m) {
   FDEM_CUDA_TRY(cudaMemcpy(&st, m->d_state, sizeof(st), cudaMemcpyDeviceToHost));
   m->geom = st.geom;
   m->geom_stale = false;
+  apply_state_flags(m, st.flags);
   return FDEM_OK;
+}
+
+// what the map API sees: hidden layers do not exist (yet).  Scans still in flight may reveal
+// one, so their results are awaited first when it matters.
+Layer* find_visible_layer(fdem_map* m, const char* name) {
+  Layer* l = find_layer(m, name);
+  if (l && l->hidden_until && m->geom_stale) (void)refresh_geometry(m);
+  return (l && !l->hidden_until) ? l : nullptr;
+}
+void settle_hidden_layers(fdem_map* m) {
+  if (!m->geom_stale) return;
+  for (auto& l : m->layers)
+    if (l.hidden_until) { (void)refresh_geometry(m); return; }
 }
 
 fdem_status push_state(fdem_map* m, uint32_t touched_count) {
   DeviceState st{};
   st.geom = m->geom;
   st.touched_count = touched_count;
+  st.flags = m->state_flags;
   FDEM_CUDA_TRY(cudaMemcpyAsync(m->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, m->stream));
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
   return FDEM_OK;
@@ -369,7 +423,16 @@ void free_scratch(fdem_mapper* mp) {
   cudaFree(mp->d_svals);
   cudaFree(mp->d_vkeys);
   cudaFree(mp->d_svkeys);
-  cudaFree(mp->d_sel);
+  cudaFree(mp->d_vk32);
+  cudaFree(mp->d_svk32);
+  cudaFree(mp->d_vv);
+  cudaFree(mp->d_svv);
+  cudaFree(mp->d_rays);
+  cudaFree(mp->d_rays_tmp);
+  cudaFree(mp->d_ray_hist);
+  mp->d_vk32 = mp->d_svk32 = mp->d_vv = mp->d_svv = nullptr;
+  mp->d_rays = mp->d_rays_tmp = nullptr;
+  mp->d_ray_hist = nullptr;
   cudaFree(mp->d_sort_temp);
   for (int i = 0; i < kStageRing; ++i) { cudaFree(mp->d_in_raw[i]); mp->d_in_raw[i] = nullptr; }
   mp->raw_cap = 0;
@@ -377,7 +440,7 @@ void free_scratch(fdem_mapper* mp) {
   mp->tb.records = nullptr;
   mp->d_pm = nullptr; mp->d_keys = mp->d_vals = nullptr;
   mp->d_skeys = mp->d_svals = nullptr; mp->d_vkeys = mp->d_svkeys = nullptr;
-  mp->d_sel = nullptr; mp->d_sort_temp = nullptr;
+  mp->d_sort_temp = nullptr;
   mp->cap = 0;
   mp->sort_temp_bytes = 0;
 }
@@ -390,6 +453,7 @@ fdem_status ensure_capacity(fdem_mapper* mp, size_t n) {
   }
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));  // scratch may still be in use
   if (mp->copy_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->copy_stream));
+  if (mp->aux_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->aux_stream));
   const size_t cap = std::max<size_t>(std::max(n, mp->cap), 1024);
   free_scratch(mp);
   for (int i = 0; i < kStageRing; ++i) {
@@ -407,7 +471,14 @@ fdem_status ensure_capacity(fdem_mapper* mp, size_t n) {
   if (need_vox) {
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_vkeys, cap * sizeof(uint64_t)));
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_svkeys, cap * sizeof(uint64_t)));
-    FDEM_CUDA_TRY(cudaMalloc(&mp->d_sel, cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_vk32, cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_svk32, cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_vv, cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_svv, cap * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_rays, cap * sizeof(float4)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_rays_tmp, cap * sizeof(float4)));
+    FDEM_CUDA_TRY(cudaMalloc(&mp->d_ray_hist, ray_sort_scratch_words() * sizeof(uint32_t)));
+    FDEM_CUDA_TRY(cudaMemset(mp->d_ray_hist, 0, ray_sort_scratch_words() * sizeof(uint32_t)));
     temp = std::max(temp, sort_pairs_u64_temp_bytes(static_cast<uint32_t>(cap), 63));
   }
   FDEM_CUDA_TRY(cudaMalloc(&mp->d_sort_temp, temp));
@@ -475,15 +546,9 @@ EstLayers est_layers(fdem_map* m) {
   return L;
 }
 
-// scratch for the ray ordering (keys / values, unsorted + sorted, CUB temp)
-struct RayScratch {
-  uint32_t *keys, *vals, *skeys, *svals;
-  void* temp;
-  size_t temp_bytes;
-};
-fdem_status raycast_device(fdem_map* m, const fdem_config& cfg, const float origin[3],
-                           const float4* pts, const uint32_t* sel, const DeviceState* st,
-                           uint32_t n_max, uint32_t* counters, const RayScratch& rs);
+fdem_status ensure_raycast_storage(fdem_map* m, bool hidden);
+__global__ void or_state_flags_kernel(DeviceState* st, uint32_t bits) { st->flags |= bits; }
+RaycastParams raycast_params(fdem_map* m, const fdem_config& cfg, const float origin[3]);
 bool voxel_box(const fdem_config& cfg, const float* T2, float voxel, VoxelBox* box);
 fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s);
 
@@ -556,8 +621,15 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
   mark(FDEM_STAGE_H2D);
   // layers the cloud's channels need (updateIntensity / updateColor add them lazily,
   // elevation_mapping.cpp:155,169)
-  if (in.intensity || (in.layout && in.layout->off_intensity >= 0)) FDEM_TRY(ensure_layer(m, "intensity", kNaN));
-  if (in.rgb || (in.layout && in.layout->off_rgb >= 0)) FDEM_TRY(ensure_layer(m, "color", kNaN));
+  const bool has_intensity = in.intensity || (in.layout && in.layout->off_intensity >= 0);
+  const bool has_color = in.rgb || (in.layout && in.layout->off_rgb >= 0);
+  if (has_intensity) FDEM_TRY(ensure_hidden_layer(m, "intensity", kNaN, SF_INTENSITY));
+  if (has_color) FDEM_TRY(ensure_hidden_layer(m, "color", kNaN, SF_COLOR));
+  if (cfg.raycasting_enabled && in.input_frame == INPUT_SENSOR_FRAME) {
+    FDEM_REQUIRE(m->geom.row_begin == 0 && m->geom.row_end == m->geom.rows,
+                 "raycasting is not supported on a row stripe");
+    FDEM_TRY(ensure_raycast_storage(m, /*hidden=*/true));
+  }
 
   PreprocessParams pp{};
   // Inputs already on the device are used in place.  Host inputs are copied into staging
@@ -677,13 +749,13 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
     FDEM_CUDA_TRY(cudaMemsetAsync(mp->d_counters, 0, CNT_COUNT * sizeof(uint32_t), s));
     mp->counters_dirty = false;
   }
-  if (m->obstacle_full_clear) {
-    // obstacle was uploaded / edited by the caller: fall back to the reference's whole-layer
-    // clear (elevation_mapping.cpp:146) until a scan with observations has gone through.
-    // Done unconditionally: if this scan ends up without observations the reference would
-    // not clear, but then the layer content was caller-provided and undefined for the path.
-    float* ob = layer_ptr(m, "obstacle");
-    if (ob) launch_fill(ob, m->cells, kNaN, s, m->lc);
+  if (m->obstacle_full_clear && !build_only) {
+    // obstacle was uploaded / edited by the caller: the next scan WITH observations clears the
+    // whole layer like the reference (elevation_mapping.cpp:146) instead of last scan's cells.
+    // Decided on the device (a scan without observations must leave the layer alone, :116-117).
+    or_state_flags_kernel<<<1, 1, 0, s>>>(m->d_state, SF_OBSTACLE_DIRTY);
+    ++m->lc.mine;
+    m->obstacle_full_clear = false;
   }
 
   ScanLaunch& L = mp->launch;
@@ -698,6 +770,14 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
   L.cp.touched_keys = m->d_touched_keys;
   L.cp.tile_path = tile ? 1 : 0;
   L.cp.tb = mp->tb;
+  L.cp.flags_if_cells = (has_intensity ? SF_INTENSITY : 0u) | (has_color ? SF_COLOR : 0u);
+  L.cp.raycast = (cfg.raycasting_enabled && in.input_frame == INPUT_SENSOR_FRAME) ? 1 : 0;
+  if (L.cp.raycast) {
+    // applyRaycasting's isInside guard tests the float sensor origin widened to double (raycasting.cpp:230)
+    L.cp.rc_origin_x = static_cast<double>(static_cast<float>(T[12]));
+    L.cp.rc_origin_y = static_cast<double>(static_cast<float>(T[13]));
+  }
+  L.cp.obstacle_cells = m->cells;
   L.sp = ScatterParams{};
   L.sp.keys = mp->d_keys;
   L.sp.pm = mp->d_pm;
@@ -709,6 +789,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
   L.sp.st_cur = m->d_state;
   L.sp.obstacle = L.cp.obstacle;
   L.sp.touched_keys = m->d_touched_keys;
+  L.sp.obstacle_cells = m->cells;
   EstimateParams& ep = L.ep;
   ep = EstimateParams{};
   ep.sorted_keys = mp->d_skeys;
@@ -774,6 +855,52 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
     launch_preprocess_bin(pp, st_in, mp->d_counters, mp->d_pm, mp->d_keys, mp->d_vals, s, m->lc);
     mark(FDEM_STAGE_COMMIT);
     launch_commit(L.cp, st_in, st_out, mp->d_counters, L.lt, s, m->lc);
+    // ── raycasting branch (fastdem.cpp:153-159), queued BESIDE the cell reduction: voxelGrid(ANY)
+    // and the DDA read only K1's map-frame points and the committed geometry and write only
+    // scan scratch, so they run on the aux stream while scatter + K3t update the map; the
+    // branches join at the resolve kernel, the first raycasting step that touches a layer.
+    // (With stage timing on — or on the global-sort path, which shares the CUB scratch — the
+    // branch is issued on the main stream in its own stage instead.) ──
+    const bool rc_beside = raycast && tile && !mp->stage_timing;
+    cudaStream_t aux = rc_beside ? mp->aux_stream : s;
+    RaycastParams rcp{};
+    auto raycast_branch = [&]() -> fdem_status {
+      // sensor origin = (T_world_base*T_base_sensor).translation(), ray_scan = voxelGrid(points, resolution, ANY)
+      const float origin[3] = {static_cast<float>(T[12]), static_cast<float>(T[13]),
+                               static_cast<float>(T[14])};
+      const float voxel = static_cast<float>(m->geom.res);
+      if (voxel < 0.001f || voxel > 100.0f)
+        return set_error(FDEM_ERR_INVALID_ARGUMENT, "voxel_size must be in [0.001, 100]");
+      rcp = raycast_params(m, cfg, origin);
+      if (rc_beside) {
+        FDEM_CUDA_TRY(cudaEventRecord(mp->ev_geom, s));
+        FDEM_CUDA_TRY(cudaStreamWaitEvent(aux, mp->ev_geom, 0));
+      }
+      // voxelGrid(ANY): sort by voxel key.  The crop filters usually bound the kept points
+      // to a box small enough for 32-bit keys (4 radix passes instead of 8).
+      VoxelBox box{};
+      cudaError_t se = cudaSuccess;
+      const RaySortScratch rss{mp->d_ray_hist, mp->d_rays_tmp, mp->d_rays};
+      if (voxel_box(cfg, pp.T2, voxel, &box)) {
+        const int bits = box.bx + box.by + box.bz + 1;
+        launch_voxel_keys32(mp->d_pm, n, 1.0f / voxel, box, mp->d_vk32, mp->d_vv, mp->d_counters, aux, m->lc);
+        se = sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vk32, mp->d_svk32,
+                            mp->d_vv, mp->d_svv, n, bits, aux, m->lc);
+        launch_voxel_select_rays32(mp->d_svk32, mp->d_svv, n, box.invalid_key, rcp, st_out, mp->d_pm,
+                                   mp->d_counters, rss, aux, m->lc);
+      } else {
+        launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vv, aux, m->lc);
+        se = sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys, mp->d_svkeys,
+                            mp->d_vv, mp->d_svv, n, 64, aux, m->lc);
+        launch_voxel_select_rays64(mp->d_svkeys, mp->d_svv, n, rcp, st_out, mp->d_pm, mp->d_counters,
+                                   rss, aux, m->lc);
+      }
+      if (se != cudaSuccess) return set_error(FDEM_ERR_CUDA, cudaGetErrorString(se));
+      launch_raycast_dda(rcp, st_out, mp->d_rays, n, mp->d_counters, aux, m->lc);
+      if (rc_beside) FDEM_CUDA_TRY(cudaEventRecord(mp->ev_rays, aux));
+      return FDEM_OK;
+    };
+    if (rc_beside) launch_status = raycast_branch();
     mark(FDEM_STAGE_SORT);
     if (tile) {
       // L1 of the 2-level sort: one scatter pass into the bucket segments K2 allocated
@@ -787,38 +914,11 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
     if (tile) launch_tile_estimate(ep, mp->tb, mp->d_counters, st_out, L.pub, s, m->lc);
     else launch_segreduce_estimate(ep, mp->d_counters, mp->d_counters, s, m->lc);
     mark(FDEM_STAGE_RAYCAST);
-    if (raycast) {
-      // fastdem.cpp:153-159: sensor origin = (T_world_base*T_base_sensor).translation(),
-      // ray_scan = voxelGrid(points, resolution, ANY)
-      const float origin[3] = {static_cast<float>(T[12]), static_cast<float>(T[13]),
-                               static_cast<float>(T[14])};
-      const float voxel = static_cast<float>(m->geom.res);
-      if (voxel < 0.001f || voxel > 100.0f) {
-        launch_status = set_error(FDEM_ERR_INVALID_ARGUMENT, "voxel_size must be in [0.001, 100]");
-      } else {
-        // voxelGrid(ANY): sort by voxel key.  The crop filters usually bound the kept points
-        // to a box small enough for 32-bit keys (4 radix passes instead of 8).
-        VoxelBox box{};
-        cudaError_t se = cudaSuccess;
-        if (voxel_box(cfg, pp.T2, voxel, &box)) {
-          const int bits = box.bx + box.by + box.bz + 1;
-          launch_voxel_keys32(mp->d_pm, n, 1.0f / voxel, box, mp->d_keys, mp->d_vals, mp->d_counters, s, m->lc);
-          se = sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_keys, mp->d_skeys,
-                              mp->d_vals, mp->d_svals, n, bits, s, m->lc);
-          launch_voxel_select32(mp->d_skeys, mp->d_svals, n, box.invalid_key, mp->d_counters, mp->d_sel, s, m->lc);
-        } else {
-          launch_voxel_keys(mp->d_pm, n, 1.0f / voxel, mp->d_vkeys, mp->d_vals, s, m->lc);
-          se = sort_pairs_u64(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vkeys, mp->d_svkeys,
-                              mp->d_vals, mp->d_svals, n, 64, s, m->lc);
-          launch_voxel_select(mp->d_svkeys, mp->d_svals, n, mp->d_counters, mp->d_sel, s, m->lc);
-        }
-        if (se != cudaSuccess) launch_status = set_error(FDEM_ERR_CUDA, cudaGetErrorString(se));
-        if (launch_status == FDEM_OK) {
-          const RayScratch rs{mp->d_keys, mp->d_vals, mp->d_skeys, mp->d_svals, mp->d_sort_temp,
-                              mp->sort_temp_bytes};
-          launch_status = raycast_device(m, cfg, origin, mp->d_pm, mp->d_sel, st_out, n, mp->d_counters, rs);
-        }
-      }
+    if (raycast && !rc_beside && launch_status == FDEM_OK) launch_status = raycast_branch();
+    if (raycast && launch_status == FDEM_OK) {
+      // join: the map is only written here, after both the estimator and the DDA are done
+      if (rc_beside) FDEM_CUDA_TRY(cudaStreamWaitEvent(s, mp->ev_rays, 0));
+      launch_raycast_resolve(rcp, st_out, L.lt, mp->d_counters, m->cells, s, m->lc);
     }
     mark(FDEM_STAGE_COUNT);
     // counters + committed state -> host (mapped pinned memory), state made current, counters re-armed
@@ -986,6 +1086,8 @@ fdem_status ensure_batch_scratch(fdem_mapper* mp) {
     FDEM_CUDA_TRY(cudaMalloc(&mp->d_batch_counters, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     FDEM_CUDA_TRY(cudaMemset(mp->d_batch_counters, 0, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
+    cudaFree(mp->tb2.bucket_count); cudaFree(mp->tb2.bucket_offset); cudaFree(mp->tb2.bucket_cursor);
+    cudaFree(mp->tb2.bucket_list);
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_count, nb));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_offset, nb));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_cursor, nb));
@@ -1046,6 +1148,7 @@ void retarget_for_batch(fdem_mapper* mp, int i, BatchScan& b) {
   b.bp.touched_keys = m->d_touched_keys;
   b.bp.invalid_key = L.pp.invalid_key;
   b.bp.clear_policy = L.cp.clear_policy;
+  b.bp.obstacle_cells = m->cells;
 }
 
 void batch_node_args(BatchScan& b, NodeArgs out[BN_COUNT]) {
@@ -1187,13 +1290,13 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
     const ScanResult& r = m->h_result[mp->last_ticket % kResultRing];
     m->geom = r.state.geom;
     m->geom_stale = false;
+    apply_state_flags(m, r.state.flags);
     mp->last.n_input = mp->last_raw ? r.counters[CNT_FINITE] : mp->last_n;
     mp->last.n_kept = r.counters[CNT_KEPT];
     mp->last.n_cells = r.counters[CNT_CELLS];
     mp->last.n_voxels = r.counters[CNT_VOXELS];
     mp->last.integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
     mp->last.voxel_box_violations = static_cast<int32_t>(r.counters[CNT_VOX_VIOLATION]);
-    if (mp->last.n_cells > 0) m->obstacle_full_clear = false;
     adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
   }
   mp->pending = false;
@@ -1256,23 +1359,52 @@ void fdem_config_default(fdem_config* c) {
   c->move_clear_policy = FDEM_MOVE_CLEAR_ALL_LAYERS;
 }
 
+fdem_status fdem_config_validate(fdem_config* c, int32_t* n_clamped) {
+  FDEM_REQUIRE(c != nullptr, "config is null");
+  int32_t n = 0;
+  // fatal (config_fastdem.cpp:131-137)
+  if (c->kalman_min_variance >= c->kalman_max_variance)
+    return set_error(FDEM_ERR_INVALID_ARGUMENT, "mapping.kalman: min_variance >= max_variance");
+  auto fix = [&](bool bad, float& v, float to) { if (bad) { v = to; ++n; } };
+  if (c->raycasting_enabled) {  // :148-179
+    fix(c->rc_height_conflict_threshold <= 0.0f, c->rc_height_conflict_threshold, 0.05f);
+    fix(c->rc_log_odds_observed <= 0.0f, c->rc_log_odds_observed, 0.4f);
+    fix(c->rc_log_odds_ghost <= 0.0f, c->rc_log_odds_ghost, 0.2f);
+    fix(c->rc_log_odds_max <= 0.0f, c->rc_log_odds_max, 2.0f);
+    fix(c->rc_clear_threshold >= 0.0f, c->rc_clear_threshold, -1.0f);
+  }
+  fix(c->kalman_min_variance <= 0.0f, c->kalman_min_variance, 0.0001f);   // :181-187
+  fix(c->kalman_process_noise < 0.0f, c->kalman_process_noise, 0.0f);    // :188-194
+  if (c->p2_elevation_marker < 0 || c->p2_elevation_marker > 4) {        // :195-196
+    c->p2_elevation_marker = std::min(std::max(c->p2_elevation_marker, 0), 4);
+    ++n;
+  }
+  for (int i = 0; i < 5; ++i)                                            // :199-207
+    if (c->p2_dn[i] < 0.0f || c->p2_dn[i] > 1.0f) {
+      c->p2_dn[i] = std::min(std::max(c->p2_dn[i], 0.0f), 1.0f);
+      ++n;
+    }
+  for (int i = 1; i < 5; ++i)                                            // :208-216
+    if (c->p2_dn[i - 1] > c->p2_dn[i])
+      return set_error(FDEM_ERR_INVALID_ARGUMENT, "mapping.p2: markers must be sorted (dn0 <= ... <= dn4)");
+  fix(c->lidar_range_noise <= 0.0f, c->lidar_range_noise, 0.02f);        // :219-224
+  fix(c->lidar_angular_noise < 0.0f, c->lidar_angular_noise, 0.0f);      // :225-230
+  fix(c->constant_uncertainty <= 0.0f, c->constant_uncertainty, 0.1f);   // :231-237
+  fix(c->rgbd_normal_a < 0.0f, c->rgbd_normal_a, 0.0f);                  // :238-257
+  fix(c->rgbd_normal_b < 0.0f, c->rgbd_normal_b, 0.0f);
+  fix(c->rgbd_normal_c < 0.0f, c->rgbd_normal_c, 0.0f);
+  fix(c->rgbd_lateral_factor < 0.0f, c->rgbd_lateral_factor, 0.0f);
+  if (n_clamped) *n_clamped = n;
+  return FDEM_OK;
+}
+
 // ───────────────────────────── map ───────────────────────────────────────────
 
-fdem_status fdem_map_create_stripe(float width, float height, float resolution, int32_t row_begin,
-                                   int32_t row_end, int32_t device, void* stream, fdem_map** out) {
-  FDEM_REQUIRE(out != nullptr, "out is null");
-  *out = nullptr;
-  FDEM_REQUIRE(resolution > 0.0f && width > 0.0f && height > 0.0f, "bad geometry");
-  int ndev = 0;
-  FDEM_CUDA_TRY(cudaGetDeviceCount(&ndev));
-  FDEM_REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
-  FDEM_CUDA_TRY(cudaSetDevice(device));
-
-  fdem_map* m = new (std::nothrow) fdem_map();
-  if (!m) return set_error(FDEM_ERR_OUT_OF_MEMORY, "host allocation failed");
-  m->device = device;
-  // ElevationMap::setGeometry(float, float, float) widens to double, then nanoGrid
-  // setGeometry: size = round(length / res), length = size * res (elevation_map.hpp:112-116)
+// ElevationMap::setGeometry(float, float, float) widens to double, then nanoGrid setGeometry:
+// size = round(length / res), length = size * res, position = 0, start index = 0
+// (elevation_map.hpp:112-116)
+static bool make_geometry(float width, float height, float resolution, int32_t row_begin,
+                          int32_t row_end, GridGeom* out) {
   const double res = static_cast<double>(resolution);
   const double L[2] = {static_cast<double>(width), static_cast<double>(height)};
   GridGeom g{};
@@ -1287,15 +1419,14 @@ fdem_status fdem_map_create_stripe(float width, float height, float resolution, 
     row_begin = 0;
     row_end = g.rows;
   }
-  if (g.rows <= 0 || g.cols <= 0 || row_begin < 0 || row_end > g.rows || row_begin >= row_end) {
-    delete m;
-    return set_error(FDEM_ERR_INVALID_ARGUMENT, "bad size or row stripe");
-  }
+  if (g.rows <= 0 || g.cols <= 0 || row_begin < 0 || row_end > g.rows || row_begin >= row_end) return false;
   g.row_begin = row_begin;
   g.row_end = row_end;
-  m->geom = g;
-  m->cells = static_cast<size_t>(row_end - row_begin) * g.cols;
+  *out = g;
+  return true;
+}
 
+static fdem_status map_init(fdem_map* m, void* stream) {
   if (stream) {
     m->stream = static_cast<cudaStream_t>(stream);
   } else {
@@ -1310,14 +1441,38 @@ fdem_status fdem_map_create_stripe(float width, float height, float resolution, 
   FDEM_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->d_result_host), m->h_result, 0));
   for (int i = 0; i < kResultRing; ++i)
     FDEM_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_scan[i], cudaEventDisableTiming));
-  fdem_status st = push_state(m, 0);
-  if (st != FDEM_OK) return st;
+  FDEM_TRY(push_state(m, 0));
   // ElevationMap() basic layers (elevation_map.hpp:99-103), then clearAll()
-  for (const char* name : {"elevation", "elevation_min", "elevation_max"}) {
-    st = add_layer(m, name, kNaN);
-    if (st != FDEM_OK) return st;
-  }
+  for (const char* name : {"elevation", "elevation_min", "elevation_max"})
+    FDEM_TRY(add_layer(m, name, kNaN));
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return FDEM_OK;
+}
+
+fdem_status fdem_map_create_stripe(float width, float height, float resolution, int32_t row_begin,
+                                   int32_t row_end, int32_t device, void* stream, fdem_map** out) {
+  FDEM_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  FDEM_REQUIRE(resolution > 0.0f && width > 0.0f && height > 0.0f, "bad geometry");
+  int ndev = 0;
+  FDEM_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  FDEM_REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
+  GridGeom g{};
+  if (!make_geometry(width, height, resolution, row_begin, row_end, &g))
+    return set_error(FDEM_ERR_INVALID_ARGUMENT, "bad size or row stripe");
+  DeviceGuard dg(device);  // the caller's current device is left as it was
+  FDEM_REQUIRE(dg.ok, "cannot select the device");
+  fdem_map* m = new (std::nothrow) fdem_map();
+  if (!m) return set_error(FDEM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  m->device = device;
+  m->geom = g;
+  m->cells = static_cast<size_t>(g.row_end - g.row_begin) * g.cols;
+  const fdem_status st = map_init(m, stream);
+  if (st != FDEM_OK) {
+    const std::string why = g_last_error;
+    fdem_map_destroy(m);  // tolerates the members that were never created
+    return set_error(st, why);
+  }
   *out = m;
   return FDEM_OK;
 }
@@ -1330,7 +1485,14 @@ fdem_status fdem_map_create(float width, float height, float resolution, int32_t
 fdem_status fdem_map_destroy(fdem_map* m) {
   if (!m) return FDEM_OK;
   DeviceGuard dg(m->device);
-  cudaStreamSynchronize(m->stream);
+  // a FastDEM still bound to this map must not be left with a dangling pointer: it is detached
+  // (its calls then fail with FDEM_ERR_INVALID_ARGUMENT; fdem_mapper_destroy stays valid)
+  for (fdem_mapper* mp : m->mappers) {
+    cudaStreamSynchronize(m->stream);
+    mp->map = nullptr;
+  }
+  m->mappers.clear();
+  if (m->stream) cudaStreamSynchronize(m->stream);
   for (auto& l : m->layers) cudaFree(l.d);
   cudaFree(m->d_state);
   cudaFree(m->d_flag);
@@ -1345,8 +1507,60 @@ fdem_status fdem_map_destroy(fdem_map* m) {
   cudaFreeHost(m->h_result);
   for (cudaEvent_t e : m->ev_scan)
     if (e) cudaEventDestroy(e);
-  if (m->own_stream) cudaStreamDestroy(m->stream);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+  (void)cudaGetLastError();
   delete m;
+  return FDEM_OK;
+}
+
+static fdem_status mapper_resize_for_map(fdem_mapper* mp);
+
+// GridMap::setGeometry + clearAll (elevation_map.hpp:112-116) IN PLACE: same handle, every
+// existing layer is re-allocated for the new size and reset to NaN, position / start index
+// return to 0.  FastDEM objects bound to the map stay valid (the reference's FastDEM holds an
+// ElevationMap& and io::loadNpz calls setGeometry on it, io_npz.cpp:440-): their map-sized
+// scratch is rebuilt here.
+fdem_status fdem_map_set_geometry(fdem_map* m, float width, float height, float resolution) {
+  FDEM_REQUIRE(m, "null map");
+  FDEM_REQUIRE(resolution > 0.0f && width > 0.0f && height > 0.0f, "bad geometry");
+  DeviceGuard dg(m->device);
+  FDEM_REQUIRE(m->geom.row_begin == 0 && m->geom.row_end == m->geom.rows,
+               "setGeometry is not valid on a row stripe");
+  GridGeom g{};
+  if (!make_geometry(width, height, resolution, -1, -1, &g))
+    return set_error(FDEM_ERR_INVALID_ARGUMENT, "bad size");
+  FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  for (fdem_mapper* mp : m->mappers) {
+    if (mp->copy_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->copy_stream));
+    if (mp->aux_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->aux_stream));
+  }
+  const size_t cells = static_cast<size_t>(g.rows) * g.cols;
+  if (cells != m->cells) {
+    for (auto& l : m->layers) {
+      cudaFree(l.d);
+      l.d = nullptr;
+      FDEM_CUDA_TRY(cudaMalloc(&l.d, std::max<size_t>(cells, 1) * sizeof(float)));
+    }
+    // map-sized scratch is re-created on demand
+    cudaFree(m->d_ray_min_enc); m->d_ray_min_enc = nullptr;
+    cudaFree(m->d_hits); m->d_hits = nullptr;
+    cudaFree(m->d_tmp[0]); cudaFree(m->d_tmp[1]); m->d_tmp[0] = m->d_tmp[1] = nullptr;
+    cudaFree(m->d_pack_cols); m->d_pack_cols = nullptr;
+    ++m->layer_epoch;
+  } else if (m->d_ray_min_enc) {
+    launch_fill_u32(m->d_ray_min_enc, cells, 0u, m->stream, m->lc);
+    launch_fill_u32(m->d_hits, cells, 0u, m->stream, m->lc);
+  }
+  m->cells = cells;
+  m->geom = g;
+  m->geom_stale = false;
+  m->state_flags &= ~static_cast<uint32_t>(SF_OBSTACLE_DIRTY);
+  m->obstacle_full_clear = false;
+  for (auto& l : m->layers) launch_fill(l.d, m->cells, kNaN, m->stream, m->lc);
+  FDEM_CUDA_TRY(cudaGetLastError());
+  FDEM_TRY(push_state(m, 0));  // touched list empty: nothing of the old map survives
+  FDEM_CUDA_TRY(cudaMemcpy(m->d_state + 1, m->d_state, sizeof(DeviceState), cudaMemcpyDeviceToDevice));
+  for (fdem_mapper* mp : m->mappers) FDEM_TRY(mapper_resize_for_map(mp));
   return FDEM_OK;
 }
 
@@ -1454,33 +1668,47 @@ fdem_status fdem_map_get_cell_position(fdem_map* m, int32_t row, int32_t col, do
 
 fdem_status fdem_map_layer_exists(fdem_map* m, const char* name, int32_t* exists) {
   FDEM_REQUIRE(m && name && exists, "null argument");
-  *exists = find_layer(m, name) ? 1 : 0;
+  DeviceGuard dg(m->device);
+  *exists = find_visible_layer(m, name) ? 1 : 0;
   return FDEM_OK;
 }
 
 fdem_status fdem_map_layer_add(fdem_map* m, const char* name, float fill) {
   FDEM_REQUIRE(m && name && name[0], "null argument");
   DeviceGuard dg(m->device);
+  if (Layer* l = find_layer(m, name)) l->hidden_until = 0;  // GridMap::add on an existing name refills it
   return add_layer(m, name, fill);
 }
 
 fdem_status fdem_map_layer_count(fdem_map* m, int32_t* count) {
   FDEM_REQUIRE(m && count, "null argument");
-  *count = static_cast<int32_t>(m->layers.size());
+  DeviceGuard dg(m->device);
+  settle_hidden_layers(m);
+  int32_t n = 0;
+  for (const auto& l : m->layers) n += l.hidden_until ? 0 : 1;
+  *count = n;
   return FDEM_OK;
 }
 
 fdem_status fdem_map_layer_name(fdem_map* m, int32_t i, char* buf, int32_t cap) {
   FDEM_REQUIRE(m && buf && cap > 0, "null argument");
-  FDEM_REQUIRE(i >= 0 && i < static_cast<int32_t>(m->layers.size()), "layer index out of range");
-  std::snprintf(buf, cap, "%s", m->layers[i].name.c_str());
-  return FDEM_OK;
+  DeviceGuard dg(m->device);
+  settle_hidden_layers(m);
+  int32_t k = 0;
+  for (const auto& l : m->layers) {
+    if (l.hidden_until) continue;
+    if (k++ == i) {
+      std::snprintf(buf, cap, "%s", l.name.c_str());
+      return FDEM_OK;
+    }
+  }
+  return set_error(FDEM_ERR_INVALID_ARGUMENT, "layer index out of range");
 }
 
 fdem_status fdem_map_layer_download(fdem_map* m, const char* name, float* dst) {
   FDEM_REQUIRE(m && name && dst, "null argument");
   DeviceGuard dg(m->device);
-  Layer* l = find_layer(m, name);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   FDEM_CUDA_TRY(cudaMemcpyAsync(dst, l->d, m->cells * sizeof(float), cudaMemcpyDefault, m->stream));
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -1490,7 +1718,7 @@ fdem_status fdem_map_layer_download(fdem_map* m, const char* name, float* dst) {
 fdem_status fdem_map_layer_upload(fdem_map* m, const char* name, const float* src) {
   FDEM_REQUIRE(m && name && src, "null argument");
   DeviceGuard dg(m->device);
-  Layer* l = find_layer(m, name);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   FDEM_CUDA_TRY(cudaMemcpyAsync(l->d, src, m->cells * sizeof(float), cudaMemcpyDefault, m->stream));
   FDEM_CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -1500,7 +1728,8 @@ fdem_status fdem_map_layer_upload(fdem_map* m, const char* name, const float* sr
 
 fdem_status fdem_map_layer_device_ptr(fdem_map* m, const char* name, float** dptr) {
   FDEM_REQUIRE(m && name && dptr, "null argument");
-  Layer* l = find_layer(m, name);
+  DeviceGuard dg(m->device);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   *dptr = l->d;
   if (l->name == "obstacle") m->obstacle_full_clear = true;  // caller may write through it
@@ -1518,7 +1747,7 @@ static fdem_status cell_offset(fdem_map* m, int32_t row, int32_t col, int64_t* l
 fdem_status fdem_map_cell_get(fdem_map* m, const char* name, int32_t row, int32_t col, float* v) {
   FDEM_REQUIRE(m && name && v, "null argument");
   DeviceGuard dg(m->device);
-  Layer* l = find_layer(m, name);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   int64_t lin;
   FDEM_TRY(cell_offset(m, row, col, &lin));
@@ -1530,7 +1759,7 @@ fdem_status fdem_map_cell_get(fdem_map* m, const char* name, int32_t row, int32_
 fdem_status fdem_map_cell_set(fdem_map* m, const char* name, int32_t row, int32_t col, float v) {
   FDEM_REQUIRE(m && name, "null argument");
   DeviceGuard dg(m->device);
-  Layer* l = find_layer(m, name);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   int64_t lin;
   FDEM_TRY(cell_offset(m, row, col, &lin));
@@ -1543,7 +1772,7 @@ fdem_status fdem_map_cell_set(fdem_map* m, const char* name, int32_t row, int32_
 fdem_status fdem_map_clear(fdem_map* m, const char* name) {
   FDEM_REQUIRE(m && name, "null argument");
   DeviceGuard dg(m->device);
-  Layer* l = find_layer(m, name);
+  Layer* l = find_visible_layer(m, name);
   if (!l) return set_error(FDEM_ERR_NO_LAYER, std::string("no such layer: ") + name);
   launch_fill(l->d, m->cells, kNaN, m->stream, m->lc);
   FDEM_CUDA_TRY(cudaGetLastError());
@@ -1593,6 +1822,38 @@ void* fdem_map_stream(fdem_map* m) { return m ? m->stream : nullptr; }
 
 // ───────────────────────────── mapper ────────────────────────────────────────
 
+// (re)build everything in the mapper that is sized by the map: bucket tables of both scratch
+// sets, graphs.  Called at creation and after fdem_map_set_geometry.
+static fdem_status mapper_resize_for_map(fdem_mapper* mp) {
+  fdem_map* map = mp->map;
+  destroy_scan_graph(mp);
+  destroy_batch_graph(mp);
+  for (TileBuffers* tb : {&mp->tb, &mp->tb2}) {
+    cudaFree(tb->bucket_count); cudaFree(tb->bucket_offset); cudaFree(tb->bucket_cursor); cudaFree(tb->bucket_list);
+    tb->bucket_count = tb->bucket_offset = tb->bucket_cursor = nullptr;
+    tb->bucket_list = nullptr;
+  }
+  // the second scratch set / state ring of batched integration is rebuilt on its next use
+  cudaFree(mp->d_ring); mp->d_ring = nullptr;
+  cudaFree(mp->d_move); mp->d_move = nullptr;
+  cudaFree(mp->d_batch_counters); mp->d_batch_counters = nullptr;
+  cudaFreeHost(mp->h_batch_counters); mp->h_batch_counters = nullptr;
+  const uint32_t bits = mp->tb.bucket_bits;
+  mp->max_buckets = static_cast<uint32_t>((map->cells + 255u) >> 8);
+  mp->tb.n_buckets = static_cast<uint32_t>((map->cells + (1ull << bits) - 1) >> bits);
+  const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_count, nb));
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_offset, nb));
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_cursor, nb));
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_list, nb * 4));
+  mp->tile_dirty = true;
+  mp->counters_dirty = true;
+  mp->cached_epoch = ~0ull;
+  mp->last_had_work = false;
+  // setGeometry + clearAll leaves the estimator layers in place, all NaN (they exist already)
+  return ensure_estimator_layers(map, mp->cfg);
+}
+
 fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mapper** out) {
   FDEM_REQUIRE(map && out, "null argument");
   *out = nullptr;
@@ -1603,6 +1864,7 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
   fdem_mapper* mp = new (std::nothrow) fdem_mapper();
   if (!mp) return set_error(FDEM_ERR_OUT_OF_MEMORY, "host allocation failed");
   mp->map = map;
+  mp->device = map->device;
   mp->cfg = c;
   fdem_status st = ensure_estimator_layers(map, c);
   if (st != FDEM_OK) { delete mp; return st; }
@@ -1615,6 +1877,15 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
     if (e3 != cudaSuccess) {
       fdem_mapper_destroy(mp);
       return set_error(FDEM_ERR_CUDA, std::string("copy stream setup failed: ") + cudaGetErrorString(e3));
+    }
+  }
+  {
+    cudaError_t e4 = cudaStreamCreateWithFlags(&mp->aux_stream, cudaStreamNonBlocking);
+    if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&mp->ev_geom, cudaEventDisableTiming);
+    if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&mp->ev_rays, cudaEventDisableTiming);
+    if (e4 != cudaSuccess) {
+      fdem_mapper_destroy(mp);
+      return set_error(FDEM_ERR_CUDA, std::string("aux stream setup failed: ") + cudaGetErrorString(e4));
     }
   }
   {
@@ -1634,18 +1905,19 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
       const int v = std::atoi(benv);
       if (v >= 8 && v <= 10) { bits = static_cast<uint32_t>(v); mp->bucket_bits_auto = false; }
     }
-    mp->max_buckets = static_cast<uint32_t>((map->cells + 255u) >> 8);
     mp->tb.bucket_bits = bits;
-    mp->tb.n_buckets = static_cast<uint32_t>((map->cells + (1ull << bits) - 1) >> bits);
-    const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
-    cudaError_t e2 = cudaMalloc(&mp->tb.bucket_count, nb);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_offset, nb);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_cursor, nb);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&mp->tb.bucket_list, nb * 4);
-    if (e2 == cudaSuccess) e2 = static_cast<cudaError_t>(tile_estimate_configure());
+    mp->device = map->device;
+    cudaError_t e2 = static_cast<cudaError_t>(tile_estimate_configure());
     if (e2 != cudaSuccess) {
       fdem_mapper_destroy(mp);
       return set_error(FDEM_ERR_CUDA, std::string("tile path setup failed: ") + cudaGetErrorString(e2));
+    }
+    map->mappers.push_back(mp);
+    const fdem_status rs = mapper_resize_for_map(mp);
+    if (rs != FDEM_OK) {
+      const std::string why = g_last_error;
+      fdem_mapper_destroy(mp);
+      return set_error(rs, why);
     }
   }
   *out = mp;
@@ -1654,10 +1926,18 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
 
 fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   if (!mp) return FDEM_OK;
-  DeviceGuard dg(mp->map->device);
-  cudaStreamSynchronize(mp->map->stream);
+  DeviceGuard dg(mp->device);
+  if (mp->map) {
+    cudaStreamSynchronize(mp->map->stream);
+    auto& v = mp->map->mappers;
+    v.erase(std::remove(v.begin(), v.end(), mp), v.end());
+  }
   if (mp->copy_stream) cudaStreamSynchronize(mp->copy_stream);
+  if (mp->aux_stream) cudaStreamSynchronize(mp->aux_stream);
   free_scratch(mp);
+  if (mp->ev_geom) cudaEventDestroy(mp->ev_geom);
+  if (mp->ev_rays) cudaEventDestroy(mp->ev_rays);
+  if (mp->aux_stream) cudaStreamDestroy(mp->aux_stream);
   destroy_scan_graph(mp);
   destroy_batch_graph(mp);
   cudaFree(mp->d_pm2);
@@ -1686,6 +1966,7 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
 }
 
 fdem_status fdem_mapper_set_config(fdem_mapper* mp, const fdem_config* cfg) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && cfg, "null argument");
   FDEM_TRY(validate_config(cfg));
   DeviceGuard dg(mp->map->device);
@@ -1696,6 +1977,7 @@ fdem_status fdem_mapper_set_config(fdem_mapper* mp, const fdem_config* cfg) {
 }
 
 fdem_status fdem_mapper_get_config(fdem_mapper* mp, fdem_config* out) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && out, "null argument");
   *out = mp->cfg;
   return FDEM_OK;
@@ -1704,6 +1986,7 @@ fdem_status fdem_mapper_get_config(fdem_mapper* mp, fdem_config* out) {
 static fdem_status integrate_common(fdem_mapper* mp, const float* xyzw, const float* cov9,
                                     const float* intensity, const uint8_t* rgb, size_t n,
                                     const double* Tbs, const double* Twb) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp, "null mapper");
   FDEM_REQUIRE(Tbs && Twb, "null transform");
   DeviceGuard dg(mp->map->device);
@@ -1731,6 +2014,7 @@ static fdem_status integrate_common(fdem_mapper* mp, const float* xyzw, const fl
 fdem_status fdem_mapper_integrate(fdem_mapper* mp, const float* xyzw, const float* intensity,
                                   const uint8_t* rgb, size_t n, const double* Tbs,
                                   const double* Twb, fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_TRY(integrate_common(mp, xyzw, nullptr, intensity, rgb, n, Tbs, Twb));
   DeviceGuard dg(mp->map->device);
   return finish_scan(mp, stats);
@@ -1740,6 +2024,7 @@ fdem_status fdem_mapper_integrate_with_cov(fdem_mapper* mp, const float* xyzw, c
                                            const float* intensity, const uint8_t* rgb, size_t n,
                                            const double* Tbs, const double* Twb,
                                            fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(cov9 || n == 0, "cov9 is null");
   FDEM_TRY(integrate_common(mp, xyzw, cov9, intensity, rgb, n, Tbs, Twb));
   DeviceGuard dg(mp->map->device);
@@ -1753,6 +2038,7 @@ static fdem_status enqueue_pointcloud2(fdem_mapper* mp, const uint8_t* data, siz
 fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
                                               const fdem_pointcloud2_layout* lo, const double* Tbs,
                                               const double* Twb, fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && lo && Tbs && Twb, "null argument");
   DeviceGuard dg(mp->map->device);
   // from_impl: empty message or no xyz fields -> empty cloud -> integrate() returns false
@@ -1769,6 +2055,7 @@ fdem_status fdem_mapper_integrate_pointcloud2(fdem_mapper* mp, const uint8_t* da
 fdem_status fdem_mapper_submit_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
                                            const fdem_pointcloud2_layout* lo, const double* Tbs,
                                            const double* Twb, uint64_t* ticket) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && lo && Tbs && Twb && ticket, "null argument");
   FDEM_REQUIRE(n > 0 && lo->off_x >= 0 && lo->off_y >= 0 && lo->off_z >= 0,
                "submit needs a non-empty cloud with x/y/z fields (integrate() returns false otherwise)");
@@ -1785,6 +2072,7 @@ fdem_status fdem_mapper_submit_pointcloud2(fdem_mapper* mp, const uint8_t* data,
 static fdem_status enqueue_pointcloud2(fdem_mapper* mp, const uint8_t* data, size_t n,
                                        const fdem_pointcloud2_layout* lo, const double* Tbs,
                                        const double* Twb) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(data, "data is null");
   FDEM_REQUIRE(lo->point_step >= 12 && (lo->point_step & 3) == 0, "point_step must be a multiple of 4");
   auto fits = [&](int32_t off, int32_t size) { return off >= 0 && off + size <= static_cast<int32_t>(lo->point_step); };
@@ -1814,12 +2102,14 @@ static fdem_status enqueue_pointcloud2(fdem_mapper* mp, const uint8_t* data, siz
 fdem_status fdem_mapper_integrate_async(fdem_mapper* mp, const float* xyzw,
                                         const float* intensity, const uint8_t* rgb, size_t n,
                                         const double* Tbs, const double* Twb) {
+  FDEM_MAPPER_ALIVE(mp);
   return integrate_common(mp, xyzw, nullptr, intensity, rgb, n, Tbs, Twb);
 }
 
 fdem_status fdem_mapper_submit(fdem_mapper* mp, const float* xyzw, const float* intensity,
                                const uint8_t* rgb, size_t n, const double* Tbs, const double* Twb,
                                uint64_t* ticket) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && ticket, "null argument");
   FDEM_REQUIRE(n > 0, "submit needs a non-empty cloud (integrate() returns false on empty input)");
   const uint64_t before = mp->map->seq;
@@ -1834,6 +2124,7 @@ fdem_status fdem_mapper_submit(fdem_mapper* mp, const float* xyzw, const float* 
 }
 
 fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && stats, "null argument");
   fdem_map* m = mp->map;
   FDEM_REQUIRE(ticket < m->seq, "unknown ticket");
@@ -1850,8 +2141,8 @@ fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stat
   if (ticket + 1 == m->seq) {  // newest scan: its committed geometry is the map's geometry
     m->geom = r.state.geom;
     m->geom_stale = false;
+    apply_state_flags(m, r.state.flags);
   }
-  if (stats->n_cells > 0) m->obstacle_full_clear = false;
   adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
   return FDEM_OK;
 }
@@ -1860,6 +2151,7 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
                                         const float* const* intensity, const uint8_t* const* rgb,
                                         const size_t* n_points, const double* Tbs, const double* Twb,
                                         fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && xyzw && n_points && Tbs && Twb, "null argument");
   FDEM_REQUIRE(n_scans >= 1 && n_scans <= kMaxBatch, "a batch holds 1 to 16 scans");
   fdem_map* m = mp->map;
@@ -1899,6 +2191,11 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
   // can still want an older slot's content: no wait here (the host keeps queueing batches while
   // the device works; fdem_mapper_wait reads the newest slot after a stream sync).
   const uint64_t ticket0 = m->seq;
+  if (m->obstacle_full_clear) {
+    or_state_flags_kernel<<<1, 1, 0, s>>>(m->d_state, SF_OBSTACLE_DIRTY);
+    ++m->lc.mine;
+    m->obstacle_full_clear = false;
+  }
   for (int i = 0; i < n_scans; ++i) {
     ScanInputs in{};
     in.xyzw = xyzw[i];
@@ -1943,6 +2240,7 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
 }
 
 fdem_status fdem_mapper_last_batch_stats(fdem_mapper* mp, fdem_scan_stats* stats, int32_t n_scans) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && stats, "null argument");
   FDEM_REQUIRE(n_scans == mp->last_batch_n && n_scans > 0, "n_scans must equal the size of the last batch");
   fdem_map* m = mp->map;
@@ -1963,6 +2261,7 @@ fdem_status fdem_mapper_last_batch_stats(fdem_mapper* mp, fdem_scan_stats* stats
 }
 
 fdem_status fdem_mapper_wait(fdem_mapper* mp, fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp, "null mapper");
   DeviceGuard dg(mp->map->device);
   return finish_scan(mp, stats);
@@ -1971,6 +2270,7 @@ fdem_status fdem_mapper_wait(fdem_mapper* mp, fdem_scan_stats* stats) {
 fdem_status fdem_mapper_update(fdem_mapper* mp, const float* xyzw, const float* var_z,
                                const float* intensity, const uint8_t* rgb, size_t n,
                                double robot_x, double robot_y, fdem_scan_stats* stats) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp, "null mapper");
   DeviceGuard dg(mp->map->device);
   if (n == 0) {
@@ -1999,6 +2299,7 @@ fdem_status fdem_mapper_update(fdem_mapper* mp, const float* xyzw, const float* 
 
 fdem_status fdem_mapper_last_preprocessed(fdem_mapper* mp, float* xyzw, float* cov9,
                                           int32_t* src_index, int64_t* n_kept) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && n_kept, "null argument");
   DeviceGuard dg(mp->map->device);
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
@@ -2026,6 +2327,7 @@ fdem_status fdem_mapper_last_preprocessed(fdem_mapper* mp, float* xyzw, float* c
 }
 
 fdem_status fdem_mapper_last_rasterized(fdem_mapper* mp, float* xyz, int64_t* n_cells) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && n_cells, "null argument");
   fdem_map* m = mp->map;
   DeviceGuard dg(m->device);
@@ -2058,7 +2360,10 @@ fdem_status fdem_mapper_last_rasterized(fdem_mapper* mp, float* xyz, int64_t* n_
   return FDEM_OK;
 }
 
-fdem_status fdem_mapper_debug_cta_times(fdem_mapper* mp, uint64_t* out1024) {
+#ifdef FDEM_PROBES
+// tuning probes (tools/phase_probe.py): exported only by a -DFDEM_PROBES build, not declared in
+// the public header
+__attribute__((visibility("default"))) fdem_status fdem_mapper_debug_cta_times(fdem_mapper* mp, uint64_t* out1024) {
   FDEM_REQUIRE(mp && out1024, "null argument");
   DeviceGuard dg(mp->map->device);
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
@@ -2067,7 +2372,7 @@ fdem_status fdem_mapper_debug_cta_times(fdem_mapper* mp, uint64_t* out1024) {
   return FDEM_OK;
 }
 
-fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* mp, int64_t* out16) {
+__attribute__((visibility("default"))) fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* mp, int64_t* out16) {
   FDEM_REQUIRE(mp && out16, "null argument");
   DeviceGuard dg(mp->map->device);
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
@@ -2077,7 +2382,10 @@ fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* mp, int64_t* out16) {
   return FDEM_OK;
 }
 
+#endif
+
 fdem_status fdem_mapper_set_cell_sort(fdem_mapper* mp, int32_t mode) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp, "null mapper");
   FDEM_REQUIRE(mode == FDEM_CELL_SORT_TILE || mode == FDEM_CELL_SORT_GLOBAL, "bad cell sort mode");
   DeviceGuard dg(mp->map->device);
@@ -2088,6 +2396,7 @@ fdem_status fdem_mapper_set_cell_sort(fdem_mapper* mp, int32_t mode) {
 }
 
 fdem_status fdem_mapper_set_stage_timing(fdem_mapper* mp, int32_t enabled) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp, "null mapper");
   DeviceGuard dg(mp->map->device);
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
@@ -2099,6 +2408,7 @@ fdem_status fdem_mapper_set_stage_timing(fdem_mapper* mp, int32_t enabled) {
 }
 
 fdem_status fdem_mapper_stage_times(fdem_mapper* mp, double* ms, int64_t* scans) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && ms && scans, "null argument");
   DeviceGuard dg(mp->map->device);
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
@@ -2113,12 +2423,14 @@ fdem_status fdem_mapper_stage_times(fdem_mapper* mp, double* ms, int64_t* scans)
 }
 
 fdem_status fdem_mapper_library_launch_count(fdem_mapper* mp, int64_t* launches) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && launches, "null argument");
   *launches = mp->map->lc.library;
   return FDEM_OK;
 }
 
 fdem_status fdem_mapper_launch_count(fdem_mapper* mp, int64_t* launches) {
+  FDEM_MAPPER_ALIVE(mp);
   FDEM_REQUIRE(mp && launches, "null argument");
   *launches = mp->map->lc.mine;
   return FDEM_OK;
@@ -2126,5 +2438,7 @@ fdem_status fdem_mapper_launch_count(fdem_mapper* mp, int64_t* launches) {
 
 }  // extern "C"
 
-// raycasting / voxel / inpainting entry points live in capi_post.cu
+// raycasting / voxel / inpainting entry points
 #include "capi_post.inc"
+// multi-GPU GLOBAL map
+#include "capi_shard.inc"

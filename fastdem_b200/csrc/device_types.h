@@ -18,6 +18,7 @@ enum Counter : int {
   CNT_FINITE = 4,    // PointCloud2 ingest: points with finite x, y, z (= cloud.size() after from())
   CNT_RC_SKIP = 5,   // 1 when raycasting preconditions failed (sensor outside map)
   CNT_VOX_VIOLATION = 6,  // points outside the host-predicted voxel box (must stay 0)
+  CNT_RAYS = 7,        // raycasting: rays in the dense list (downward representatives)
   CNT_REC_SLOTS = 8,   // tile path: record slots handed out to bucket segments
   CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
   CNT_WORK = 10,       // tile path: K3t's dynamic work counter
@@ -56,10 +57,96 @@ struct TileBuffers {
 struct DeviceState {
   GridGeom geom;
   uint32_t touched_count;  // valid entries in the touched-key list of the last scan with >=1 cell
-  uint32_t _pad;
+  // sticky facts only the device learns, carried from scan to scan (StateFlag bits): which
+  // lazily created layers the reference would have created by now, and whether the obstacle
+  // layer was written behind the mapper's back (needs the reference's whole-layer clear)
+  uint32_t flags;
+};
+enum StateFlag : uint32_t {
+  SF_INTENSITY = 1u,      // a scan carrying intensity produced >= 1 cell (elevation_mapping.cpp:154-156)
+  SF_COLOR = 2u,          // a scan carrying colour produced >= 1 cell (:168-170)
+  SF_RAYCAST = 4u,        // applyRaycasting got past its guards once (raycasting.cpp:221-240)
+  SF_OBSTACLE_DIRTY = 8u  // obstacle layer edited by the caller: next observing scan clears all of it
 };
 
 enum InputFrame : int { INPUT_SENSOR_FRAME = 0, INPUT_MAP_FRAME = 1 };
+
+// ── multi-GPU GLOBAL map: row stripes ─────────────────────────────────
+// One logical map, `world` stripes of consecutive logical rows, one per rank / GPU: the first
+// `extra` stripes hold base + 1 rows, the others base (fastdem_b200/sharded.py stripe_bounds).
+// A scan is integrated in two halves.  FRONT (every rank, on its 1/world slice of the scan's
+// points, read in place from the ingest GPU over NVLink): K1 + bucket partition, with
+// owner-major cell keys  key = stripe * stride + (col * rows_of_stripe + row_in_stripe), so a
+// 1024-key bucket never straddles two stripes; the records stay in the source rank's memory.
+// BACK (every rank, for the buckets of its own stripe): pull the bucket's record pieces from
+// all `world` sources over NVLink (TMA bulk reads of peer memory) and run K3t.  Two flags per
+// pair of ranks order the halves (ready: source -> owner, consumed: owner -> source); there is
+// no collective and no host round trip on the data path.
+constexpr int kMaxShards = 8;
+
+struct ShardGeom {
+  int32_t world, rank;     // world <= 1: unsharded
+  int32_t base, extra;     // rows / world, rows % world
+  uint32_t stride;         // key stride between stripes (cells of the largest stripe, rounded up to 1024)
+};
+
+// stripe that owns logical row `row`, its first row and its row count
+FDEM_HD int32_t shard_of_row(const ShardGeom& sg, int32_t row, int32_t& row_begin, int32_t& rows_local) {
+  const int32_t big = sg.extra * (sg.base + 1);
+  if (row < big) {
+    const int32_t d = row / (sg.base + 1);
+    row_begin = d * (sg.base + 1);
+    rows_local = sg.base + 1;
+    return d;
+  }
+  const int32_t d = sg.extra + (row - big) / sg.base;
+  row_begin = big + (d - sg.extra) * sg.base;
+  rows_local = sg.base;
+  return d;
+}
+
+// what a source rank publishes for the owners, and the flags of the two-way handshake; lives at
+// the start of every rank's exchange arena (peer-mapped by all other ranks)
+struct ShardHeader {
+  uint32_t ready[kMaxShards];        // [s] written by source s: front half of scan #ready[s] is complete
+  uint32_t consumed[kMaxShards];     // [d] written by owner d: it has finished reading scan #consumed[d]
+  uint32_t inside[2][kMaxShards];    // [scan parity][s]: points of source s's slice inside the map
+  uint32_t _pad[32];
+};
+
+// one non-empty bucket of this rank's stripe: where its records lie in every source's arena
+struct ShardJob {
+  uint32_t bucket;                   // bucket index inside the stripe
+  uint32_t total;                    // records over all sources
+  uint32_t off[kMaxShards];          // first record slot in source s's record buffer
+  uint32_t cnt[kMaxShards];
+};
+
+struct ShardFrontArgs {              // source side, after the scatter: publish to the owners
+  ShardHeader* peer_hdr[kMaxShards];
+  uint32_t seq;
+  int32_t world, rank;
+};
+
+struct ShardBackArgs {               // owner side
+  ShardHeader* hdr;                            // this rank's header (flags written by the peers)
+  ShardHeader* peer_hdr[kMaxShards];           // consumed[] is written back to every source
+  const uint32_t* peer_cursor[kMaxShards];     // source s's record count per (global) bucket, this scan's parity
+  const uint32_t* peer_offset[kMaxShards];     // source s's first record slot per bucket
+  const CellRecord* peer_records[kMaxShards];  // source s's record buffer, this scan's parity
+  ShardJob* jobs;                              // [buckets per stripe]
+  uint32_t seq;
+  int32_t world, rank;
+  uint32_t bps;                                // buckets per stripe (= stride >> 10)
+  // map-side bookkeeping the back half owns (obstacle reset, touched-list hand-over, state flags)
+  const DeviceState* st_cur;
+  DeviceState* st_out;
+  float* obstacle;
+  const uint32_t* touched_keys;
+  uint32_t invalid_key;
+  uint32_t flags_if_cells;
+  size_t obstacle_cells;
+};
 
 // everything K1 needs for one scan (fastdem::Config + the two transforms, pre-cast on the
 // host exactly as the reference casts them: Isometry3d::matrix().cast<float>(),
@@ -97,6 +184,7 @@ struct PreprocessParams {
   float* out_intensity;
   uint8_t* out_rgb;
   int32_t raw_vec16;  // 16-byte points with x, y, z at 0, 4, 8 and one 4-byte channel at 12, base 16-B aligned
+  ShardGeom shard;    // world > 1: owner-major keys for every stripe (multi-GPU front half)
 };
 
 // pointers to every layer the estimator kernel reads or writes (null when absent)
@@ -154,6 +242,12 @@ struct CommitParams {
   MoveRecord* move_out;
   int32_t tile_path;  // 1: also hand out bucket segments (TileBuffers) and let K3t count cells
   TileBuffers tb;
+  // StateFlag bookkeeping: bits to set when this scan produces >= 1 cell (its channels), and the
+  // raycasting guards (enabled; sensor origin, tested against the committed geometry)
+  uint32_t flags_if_cells;
+  int32_t raycast;
+  double rc_origin_x, rc_origin_y;
+  size_t obstacle_cells;  // cells in the obstacle layer (whole-layer clear when SF_OBSTACLE_DIRTY)
 };
 
 struct ScatterParams {
@@ -168,6 +262,8 @@ struct ScatterParams {
   const DeviceState* st_cur;
   float* obstacle;
   const uint32_t* touched_keys;
+  size_t obstacle_cells;
+  uint32_t index_base;  // point index of element 0 (multi-GPU: the slice's offset in the scan)
 };
 
 // back prologue of a scan in a batch: the map writes the commit / scatter kernels do in the
@@ -181,6 +277,7 @@ struct BackParams {
   const uint32_t* touched_keys;
   uint32_t invalid_key;
   int32_t clear_policy;
+  size_t obstacle_cells;
 };
 
 // what K3t's last CTA needs to end the scan (publish); all null/0 when a separate
@@ -199,7 +296,7 @@ struct RaycastParams {
   float* raycasting;    // per-scan min ray height (NaN = not traversed)
   float* logodds;       // _visibility_logodds
   float* ghost_removal;
-  uint32_t* ray_min_enc;  // scratch, one u32 per cell: order-preserving encoding for atomicMin
+  uint32_t* ray_min_enc;  // scratch, one u32 per LOGICAL cell: bits of the lowest ray's (height - sensor z) <= -0; 0 = none
   uint32_t* hits;         // scratch, one u32 per cell: observed-evidence hit counts
 };
 
@@ -241,9 +338,21 @@ void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounte
 void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
                           DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
                           LaunchCounter& lc);
-int tile_estimate_debug_clocks(long long* out16);
-int tile_estimate_debug_cta_ns(unsigned long long* out1024);  // entry/exit ns of the first 512 CTAs  // CTA 0 phase clocks of the last K3t launch
+#ifdef FDEM_PROBES
+int tile_estimate_debug_clocks(long long* out16);             // CTA 0 phase clocks of the last K3t launch
+int tile_estimate_debug_cta_ns(unsigned long long* out1024);  // entry/exit ns of the first 512 CTAs
+#endif
 int tile_estimate_configure();  // one-time cudaFuncSetAttribute (dynamic smem); returns cudaError_t
+// multi-GPU GLOBAL map (kernels_tile.cu)
+void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, uint32_t* zero_a, uint32_t* zero_b,
+                        size_t n_words, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
+                                LaunchCounter& lc);
+void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_tile_estimate_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
+                                DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
+                                LaunchCounter& lc);
 void launch_move_only(const DeviceState* st_in, DeviceState* st_out, double x, double y,
                       int clear_policy, const LayerTable& lt, uint32_t* moved_flag, cudaStream_t s,
                       LaunchCounter& lc);
@@ -265,13 +374,24 @@ void launch_voxel_keys32(const float4* pm, uint32_t n, float inv_voxel, const Vo
 void launch_voxel_select32(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
                            uint32_t invalid_key, uint32_t* counters, uint32_t* out_sel,
                            cudaStream_t s, LaunchCounter& lc);
-int ray_key_bits();
-void launch_ray_keys(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                     const uint32_t* sel, uint32_t n_max, uint32_t* counters, uint32_t* rkeys,
-                     uint32_t* rvals, cudaStream_t s, LaunchCounter& lc);
-void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                         const uint32_t* rkeys, const uint32_t* rvals, uint32_t n_max,
-                         cudaStream_t s, LaunchCounter& lc);
+// voxel representative + observed-evidence hits + list of the rays to trace, counting-sorted
+// into (length, azimuth) bundles (sorted_keys == nullptr: every input point is a ray_scan point)
+struct RaySortScratch {
+  uint32_t* hist;      // [ray_sort_scratch_words()]: histogram (all zero between scans) + cursors
+  float4* unsorted;    // [n] ray end points in discovery order, ordering key in .w
+  float4* rays;        // [n] the sorted list the DDA kernel reads
+};
+size_t ray_sort_scratch_words();
+void launch_voxel_select_rays32(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                                uint32_t invalid_key, const RaycastParams& p, const DeviceState* st,
+                                const float4* pts, uint32_t* counters, const RaySortScratch& rs,
+                                cudaStream_t s, LaunchCounter& lc);
+void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                                const RaycastParams& p, const DeviceState* st, const float4* pts,
+                                uint32_t* counters, const RaySortScratch& rs, cudaStream_t s,
+                                LaunchCounter& lc);
+void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
+                        uint32_t n_max, const uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,
                             const uint32_t* counters, size_t n_cells, cudaStream_t s,
                             LaunchCounter& lc);

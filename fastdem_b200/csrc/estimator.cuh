@@ -165,7 +165,9 @@ __device__ __forceinline__ void kalman_cell(const EstimateParams& p, uint32_t c,
     const float K = P / (P + R);
     x = x + K * (z - x);
     P = (1.0f - K) * P;
-    P = fminf(fmaxf(P, p.kalman_min_variance), p.kalman_max_variance);
+    // std::clamp(P, min, max) exactly (kalman_estimation.hpp:124): a NaN P stays NaN
+    P = (P < p.kalman_min_variance) ? p.kalman_min_variance
+                                    : ((p.kalman_max_variance < P) ? p.kalman_max_variance : P);
     count += 1.0f;
   }
   if (isnan(mean)) {

@@ -242,10 +242,20 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
     if (kept) {
       int32_t row, col;
       if (geom_get_index(sg, static_cast<double>(q.x), static_cast<double>(q.y), row, col)) {
-        const int64_t lin = geom_linear(sg, row, col);
-        if (lin >= 0) {
-          key = static_cast<uint32_t>(lin);
+        if (p.shard.world > 1) {
+          // multi-GPU front half: this rank bins its slice of the scan for EVERY stripe
+          // (owner-major keys; stripes exist only for GLOBAL maps, buffer row == logical row)
+          int32_t rb, rl;
+          const int32_t d = shard_of_row(p.shard, row, rb, rl);
+          key = static_cast<uint32_t>(d) * p.shard.stride +
+                static_cast<uint32_t>(col) * static_cast<uint32_t>(rl) + static_cast<uint32_t>(row - rb);
           inside = true;
+        } else {
+          const int64_t lin = geom_linear(sg, row, col);
+          if (lin >= 0) {
+            key = static_cast<uint32_t>(lin);
+            inside = true;
+          }
         }
       }
       pm[i] = make_float4(q.x, q.y, q.z, var_z);
@@ -284,6 +294,25 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
 }
 
 // ───────────────────────────── K2: commit / move / clear ─────────────────────
+
+// updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146).  Only cells the last
+// observing scan touched can hold a value, so only those are reset — unless the caller wrote
+// the layer behind the mapper's back (SF_OBSTACLE_DIRTY): then the whole layer is cleared, as
+// the reference does.  Runs only when this scan has observations (update() returns early
+// otherwise, :116-117).
+__device__ __forceinline__ void reset_obstacle(float* __restrict__ obstacle,
+                                               const uint32_t* __restrict__ touched_keys,
+                                               uint32_t n_prev, uint32_t invalid_key, bool dirty,
+                                               size_t cells, size_t tid, size_t nthreads) {
+  if (dirty) {
+    for (size_t c = tid; c < cells; c += nthreads) obstacle[c] = nan_f32();
+    return;
+  }
+  for (size_t j = tid; j < n_prev; j += nthreads) {
+    const uint32_t k = touched_keys[j];
+    if (k != invalid_key) obstacle[k] = nan_f32();
+  }
+}
 
 // vacated rows / columns (or the whole map) -> NaN on the selected layers.  The
 // (layer, cell) space is flattened so the stores spread evenly over the threads.
@@ -386,13 +415,10 @@ commit_move_clear_kernel(const __grid_constant__ CommitParams p,
     // cells that can hold a value: those the last observing scan touched.  Runs only when
     // this scan has observations (update() returns early otherwise, :116-117).
     if (s_inside > 0 && p.obstacle) {
-      const uint32_t prev = st_in->touched_count;
       const size_t tid = static_cast<size_t>(blockIdx.x - nA) * blockDim.x + threadIdx.x;
-      const size_t nthreads = static_cast<size_t>(nB) * blockDim.x;
-      for (size_t j = tid; j < prev; j += nthreads) {
-        const uint32_t k = p.touched_keys[j];
-        if (k != p.invalid_key) p.obstacle[k] = nan_f32();
-      }
+      reset_obstacle(p.obstacle, p.touched_keys, st_in->touched_count, p.invalid_key,
+                     (st_in->flags & SF_OBSTACLE_DIRTY) != 0, p.obstacle_cells, tid,
+                     static_cast<size_t>(nB) * blockDim.x);
     }
     return;
   }
@@ -410,6 +436,12 @@ commit_move_clear_kernel(const __grid_constant__ CommitParams p,
     if (p.local_mode && kept > 0) g_new = geom_move(g_old, p.robot_x, p.robot_y, mr);
     if (blockIdx.x == nA + nB) {
       st_out->geom = g_new;
+      // sticky facts (StateFlag): layers the reference has created lazily by now; the
+      // caller-edited obstacle layer is clean again once an observing scan has cleared it
+      uint32_t flags = st_in->flags;
+      if (s_inside > 0) flags = (flags | p.flags_if_cells) & ~static_cast<uint32_t>(SF_OBSTACLE_DIRTY);
+      if (p.raycast && kept > 0 && geom_is_inside(g_new, p.rc_origin_x, p.rc_origin_y)) flags |= SF_RAYCAST;
+      st_out->flags = flags;
       if (p.defer) {
         // batched integration: the map writes (and the touched-count hand-over, which the
         // previous scan's estimator may still be producing) belong to back_prologue_kernel
@@ -448,11 +480,9 @@ back_prologue_kernel(const __grid_constant__ BackParams p, const __grid_constant
   if (blockIdx.x < nB) {
     if (n_inside > 0 && p.obstacle) {
       const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-      const size_t nthreads = static_cast<size_t>(nB) * blockDim.x;
-      for (size_t j = tid; j < prev; j += nthreads) {
-        const uint32_t k = p.touched_keys[j];
-        if (k != p.invalid_key) p.obstacle[k] = nan_f32();
-      }
+      reset_obstacle(p.obstacle, p.touched_keys, prev, p.invalid_key,
+                     (p.st_cur->flags & SF_OBSTACLE_DIRTY) != 0, p.obstacle_cells, tid,
+                     static_cast<size_t>(nB) * blockDim.x);
     }
     return;
   }
@@ -499,6 +529,7 @@ move_only_kernel(const DeviceState* __restrict__ st_in, DeviceState* __restrict_
     if (blockIdx.x == 0) {
       st_out->geom = g_new;
       st_out->touched_count = st_in->touched_count;
+      st_out->flags = st_in->flags;
       *moved_flag = mr.moved;
     }
   }

@@ -3,9 +3,8 @@
 //   applyRaycasting                      fastdem/src/raycasting.cpp:218-249
 // plus the 3x3 inpainting stencil (fastdem/src/inpainting.cpp:21-67, a "next" row).
 //
-// Raycasting is not HBM-bound: it is a per-ray 2-D DDA whose cell visits are L2 atomics
-// (atomicMin on an order-preserving encoding of the ray height) on a per-scan scratch
-// buffer — scratch, never estimator state.  Compiled with -fmad=false; the DDA follows the
+// Raycasting is not HBM-bound: it is a per-ray 2-D DDA whose cell visits are reads of (and rare
+// atomics on) a per-scan, L2-resident scratch buffer — scratch, never estimator state.  Compiled with -fmad=false; the DDA follows the
 // reference's float32 arithmetic expression by expression.
 #include <float.h>
 #include <cstdlib>
@@ -18,21 +17,10 @@ namespace fdem {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr uint32_t kEncInit = 0xffffffffu;   // "no ray crossed this cell"
 constexpr uint32_t kNoSel = 0xffffffffu;
 constexpr uint64_t kInvalidVoxel = ~0ull;    // nanopcl::voxel::INVALID_KEY (core/voxel.hpp:26)
 
 __device__ __forceinline__ float nanf_() { return __int_as_float(0x7fc00000); }
-
-// order-preserving float -> uint map (so atomicMin on the uint is a min on the float)
-__device__ __forceinline__ uint32_t enc_f32(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float dec_f32(uint32_t e) {
-  const uint32_t u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
-  return __uint_as_float(u);
-}
 
 // voxel::pack (nanopcl/core/voxel.hpp:28-42): [z:21][y:21][x:21] of floor(p*inv) + 2^20
 __device__ __forceinline__ uint64_t voxel_pack(float x, float y, float z, float inv) {
@@ -135,85 +123,193 @@ voxel_select_kernel(const Key* __restrict__ skeys, const uint32_t* __restrict__ 
   if (threadIdx.x == 0 && heads) atomicAdd(&counters[CNT_VOXELS], static_cast<uint32_t>(heads));
 }
 
-// ── ray ordering.  Rays are handed to the DDA kernel sorted by length: a warp then holds 32
-// rays that finish together (no lanes idling while one long ray finishes, no lanes lost to
-// untraced entries).  The order has no effect on the result — every cell keeps the MINIMUM
-// over the rays that cross it. ──
-constexpr uint32_t kRayInvalid = 0xffu;
-constexpr int kRayKeyBits = 8;
+// ── processScan's per-point part, fused with the voxel-representative selection ──
+// One pass over the voxel-sorted (key, index) stream does everything raycasting.cpp:160-174
+// does per ray_scan point EXCEPT the DDA itself:
+//   * voxelGrid(ANY) representative of every voxel (voxel_grid_impl.hpp:171-172)
+//   * observed evidence: one hit count per representative that falls inside the map (the
+//     log-odds additions themselves are applied per hit, in order, by the resolve kernel)
+//   * the rays that will be traced (downward, >= 1e-4 m long in xy) are appended to a list of
+//     end points together with a 15-bit ordering key (length bin, azimuth bin) whose histogram
+//     is built on the fly — the counting sort below turns the list into BUNDLES: 32 consecutive
+//     rays of the sorted list point the same way (< 1 degree apart) and are equally long, so a
+//     warp of the DDA kernel walks 32 nearly identical rays (coalesced loads, lanes that finish
+//     together).  Order has no effect on the result: a cell keeps the MINIMUM over its rays.
+// skeys == nullptr: applyRaycasting on a caller's cloud (fdem_raycast) — every point is a ray_scan point.
+constexpr int kRayLenBins = 32;    // ray length in 32-cell bins
+constexpr int kRayAzBins = 1024;   // "diamond angle" sectors (monotone in azimuth, no atan2)
+constexpr int kRayBins = kRayLenBins * kRayAzBins;
 
-// processScan's per-point part (raycasting.cpp:160-174): the observed-evidence hit of every
-// ray_scan point, and the sort key of the points that get traced
+template <typename Key>
 __global__ void __launch_bounds__(kBlock)
-ray_keys_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
-                const float4* __restrict__ pts, const uint32_t* __restrict__ sel, uint32_t n_max,
-                uint32_t* __restrict__ counters, uint32_t* __restrict__ rkeys,
-                uint32_t* __restrict__ rvals) {
+voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restrict__ svals,
+                         uint32_t n, const Key invalid, const __grid_constant__ RaycastParams p,
+                         const DeviceState* __restrict__ st, const float4* __restrict__ pts,
+                         uint32_t* __restrict__ counters, float4* __restrict__ rays_unsorted,
+                         uint32_t* __restrict__ ray_hist) {
+  __shared__ uint32_t s_warp[kBlock / 32];
+  __shared__ uint32_t s_base;
   const GridGeom g = st->geom;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  // preconditions (raycasting.cpp:230-234): sensor origin must be inside the map
-  if (!geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]))) {
-    if (i == 0) counters[CNT_RC_SKIP] = 1;
-    if (i < n_max) rkeys[i] = kRayInvalid;
-    return;
-  }
-  if (i >= n_max) return;
-  uint32_t key = kRayInvalid;
-  uint32_t src = i;
-  if (sel) src = sel[i];
-  if (src != kNoSel) {
-    const float4 pt = __ldg(&pts[src]);
-    // observed evidence: count hits per cell; the log-odds update itself is applied once
-    // per hit, in order, by the resolve kernel (:162-170)
-    int32_t row, col;
-    if (geom_get_index(g, static_cast<double>(pt.x), static_cast<double>(pt.y), row, col))
-      atomicAdd(&p.hits[static_cast<size_t>(col) * g.rows + row], 1u);
-    const float dx = pt.x - p.origin[0];
-    const float dy = pt.y - p.origin[1];
-    const float ray_len_2d = sqrtf(dx * dx + dy * dy);
-    // upward rays are skipped (:173); rays shorter than 1e-4 m in xy are skipped (:52-53)
-    if (pt.z < p.origin[2] && ray_len_2d >= 1e-4f) {
-      // grouping only (no exactness needed): ray length in 4-cell bins, 8 bits = one radix pass
-      const int len_cells = static_cast<int>(ray_len_2d / static_cast<float>(g.res));
-      key = static_cast<uint32_t>(min(len_cells >> 2, 254));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // preconditions (raycasting.cpp:230-234): sensor origin must be inside the map; the voxel
+  // count is still reported (voxelGrid runs before applyRaycasting, fastdem.cpp:156-158)
+  const bool rc_ok = geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]));
+  if (!rc_ok && i == 0) counters[CNT_RC_SKIP] = 1;
+  bool head = false, trace = false;
+  float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (i < n) {
+    uint32_t src = kNoSel;
+    if (skeys) {
+      const Key key = skeys[i];
+      head = key != invalid && (i == 0 || skeys[i - 1] != key);
+      if (head) {
+        // end of the run of `key`: voxels hold a point or two, so walk a few elements first
+        // (coalesced with the neighbours' walks) and binary-search only a long run
+        uint32_t lo = i + 1;
+        constexpr uint32_t kWalk = 6;
+        const uint32_t wend = min(n, i + 1 + kWalk);
+        while (lo < wend && skeys[lo] == key) ++lo;
+        if (lo == wend && lo < n && skeys[lo] == key) {
+          uint32_t hi = n;
+          ++lo;
+          while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (skeys[mid] == key) lo = mid + 1; else hi = mid;
+          }
+        }
+        const uint64_t count = lo - i;
+        const uint64_t start = i;
+        src = svals[count == 1 ? start : start + (count * 7ull + start * 13ull) % count];
+      }
+    } else {
+      head = true;
+      src = i;
+    }
+    if (head && rc_ok) {
+      pt = __ldg(&pts[src]);
+      int32_t row, col;
+      if (geom_get_index(g, static_cast<double>(pt.x), static_cast<double>(pt.y), row, col))
+        atomicAdd(&p.hits[static_cast<size_t>(col) * g.rows + row], 1u);
+      const float dx = pt.x - p.origin[0];
+      const float dy = pt.y - p.origin[1];
+      const float ray_len_2d = sqrtf(dx * dx + dy * dy);
+      // upward rays are skipped (:173); rays shorter than 1e-4 m in xy are skipped (:52-53)
+      trace = pt.z < p.origin[2] && ray_len_2d >= 1e-4f;
+      if (trace) {
+        // ordering key (grouping only, no exactness needed): DDA steps ~ (|dx| + |dy|) / res
+        const float l1 = fabsf(dx) + fabsf(dy);
+        const int lenbin = min(static_cast<int>(l1 / static_cast<float>(g.res)) >> 5, kRayLenBins - 1);
+        float a = dy / l1;                        // [-1, 1]
+        if (dx < 0.0f) a = 2.0f - a;              // (1, 3]
+        else if (dy < 0.0f) a = 4.0f + a;         // [3, 4)
+        const int azbin = min(max(static_cast<int>(a * (kRayAzBins / 4)), 0), kRayAzBins - 1);
+        const uint32_t okey = static_cast<uint32_t>(lenbin * kRayAzBins + azbin);
+        pt.w = __uint_as_float(okey);
+        atomicAdd(&ray_hist[okey], 1u);
+      }
     }
   }
-  rkeys[i] = key;
-  rvals[i] = src;
+  // compaction inside the block, one atomic per block for its base (scan scratch)
+  const uint32_t tm = __ballot_sync(0xffffffffu, trace);
+  const uint32_t hm = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) s_warp[warp] = (static_cast<uint32_t>(__popc(tm)) << 16) | static_cast<uint32_t>(__popc(hm));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t rays_total = 0, heads_total = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) {
+      const uint32_t v = s_warp[w];
+      s_warp[w] = rays_total;           // exclusive prefix of the traced rays
+      rays_total += v >> 16;
+      heads_total += v & 0xffffu;
+    }
+    if (skeys && heads_total) atomicAdd(&counters[CNT_VOXELS], heads_total);
+    s_base = rays_total ? atomicAdd(&counters[CNT_RAYS], rays_total) : 0u;
+  }
+  __syncthreads();
+  if (trace) rays_unsorted[s_base + s_warp[warp] + __popc(tm & ((1u << lane) - 1u))] = pt;
+}
+
+// counting sort of the ray list by ordering key, step 2 of 3: exclusive scan of the histogram
+// (one CTA; 32 K bins), cursors out, histogram re-armed for the next scan
+__global__ void __launch_bounds__(1024)
+ray_bin_scan_kernel(uint32_t* __restrict__ ray_hist, uint32_t* __restrict__ ray_cursor) {
+  __shared__ uint32_t s_warp[32];
+  constexpr int kPer = kRayBins / 1024;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t v[kPer];
+  uint32_t t = 0;
+  uint4* h4 = reinterpret_cast<uint4*>(ray_hist) + threadIdx.x * (kPer / 4);
+#pragma unroll
+  for (int k = 0; k < kPer / 4; ++k) {
+    const uint4 q = h4[k];
+    v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    t += q.x + q.y + q.z + q.w;
+    h4[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  uint32_t inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t wprefix = 0;
+  for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
+  uint32_t base = wprefix + inc - t;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    ray_cursor[threadIdx.x * kPer + k] = base;
+    base += v[k];
+  }
+}
+
+// step 3 of 3: scatter (order inside a bin is irrelevant)
+__global__ void __launch_bounds__(kBlock)
+ray_bin_scatter_kernel(const float4* __restrict__ rays_unsorted, float4* __restrict__ rays,
+                       uint32_t* __restrict__ ray_cursor, const uint32_t* __restrict__ counters) {
+  const uint32_t n_rays = counters[CNT_RAYS];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) {
+    const float4 pt = rays_unsorted[i];
+    rays[atomicAdd(&ray_cursor[__float_as_uint(pt.w)], 1u)] = pt;
+  }
 }
 
 constexpr int kRayBatch = 8;
 
-// traceRay (raycasting.cpp:46-139): one thread per traced ray.
-//  * Rays are sorted by length so that a warp's 32 rays finish together (in input order two
-//    thirds of the lanes idle: untraced entries, and short rays waiting for the longest one).
-//  * NEAR FIELD in shared memory.  Every ray starts in the sensor's cell and most rays are
-//    short (steep beams), so most cell visits fall inside a small window around the sensor.
-//    Persistent CTAs (5 per SM) each keep a 96 x 96-cell window's minima in shared memory
-//    (36 KiB), run their rays' first steps against it (a shared-memory load + a rare shared
-//    atomic instead of an uncoalesced global load + L2 atomic), and flush the window once at
-//    the end.  (64 / 96 / 128-cell windows measured: 238 / 233 / 248 us on config 4.)
-//  * FAR FIELD batched.  Outside the window the DDA runs kRayBatch cells at a time: the cell
-//    sequence does not depend on memory, so the batch's cells and exit heights are computed
-//    first, ALL their loads issued back to back, then the compares / atomics.
-// Measured alternatives (B200, config 4, 1.05 M points):
-//   input order, one cell per round trip                                     540 us
-//   length order + batched loads, no near-field window                        260 us
-//   + near-field window (this kernel)                                          233 us
-//   (azimuth sector, length) order: loads coalesce (2 sectors per request instead of ~30)
-//     but lanes in lockstep on the same cells all see the same stale minimum and all
-//     fire: 24 M atomics instead of 6 M                                        355 us
-//   the same + per-CTA shared-memory hash table of the wedge's minima          1280 us
-template <int kNear>  // near-field window: kNear x kNear cells around the sensor
+// traceRay (raycasting.cpp:46-139): one thread per traced ray, float32 2-D DDA, expression by
+// expression as the reference.  What is stored per cell is not the ray height but its offset
+// from the sensor height, x = min(t_exit, 1) * dz <= -0 (only downward rays are traced): the
+// reference's value is fl(sz + x), float addition of a constant is monotone, so
+// min over rays of fl(sz + x_i) == fl(sz + min_i x_i) exactly — and for non-positive floats the
+// raw bit pattern grows as the value falls, so the minimum is an atomicMax on the bits, the
+// "no ray" state is 0 and no encoding arithmetic is needed in the loop.  The scratch is laid
+// out in LOGICAL cell coordinates (column-major, lin = c * nrows + r): the circular-buffer
+// wrap is paid once per cell by the resolve kernel instead of once per DDA step.
+//  * BUNDLES: the ray list is ordered (length, azimuth); warp task j = rays [32 j, 32 j + 32).
+//    Tasks are dealt to the CTAs round-robin, so every CTA (and SM) gets the same mixture of
+//    short and long bundles.
+//  * NEAR FIELD in shared memory.  Every ray starts in the sensor's cell, so the cells around
+//    the sensor see every ray: each CTA keeps a kNear x kNear window in shared memory (a shared
+//    load + a rare shared atomic instead of a global load + L2 atomic on the map's hottest
+//    words) and flushes it once at the end.
+//  * FAR FIELD batched.  The cell sequence does not depend on memory: kRayBatch cells and exit
+//    offsets are computed first, their loads issued back to back, then the compares / atomics.
+//    A stored value only moves one way, so a stale (L1-cached) read can at worst cause a
+//    needless atomic, never a missed one.  The lanes of a bundle often lower the same cell in
+//    the same step: they elect one atomic per cell (match.any + redux.max, warp-uniform).
+template <int kNear>
 __global__ void __launch_bounds__(kBlock)
-raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
-                    const float4* __restrict__ pts, const uint32_t* __restrict__ rkeys,
-                    const uint32_t* __restrict__ rvals, uint32_t n_max) {
-  extern __shared__ uint32_t near_min[];  // [kNear * kNear], column-major in LOGICAL cells
+raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
+                   const float4* __restrict__ rays, const uint32_t* __restrict__ counters) {
+  extern __shared__ uint32_t near_x[];  // [kNear * kNear], column-major in LOGICAL cells
   constexpr int kNearHalf = kNear / 2;
+  const uint32_t n_rays = counters[CNT_RAYS];
+  if (n_rays == 0) return;                // also: preconditions failed (no ray was listed)
   const GridGeom g = st->geom;
   const int nrows = g.rows, ncols = g.cols;
-  // float32 grid math, expression by expression as the reference
   const float resolution = static_cast<float>(g.res);
   const float sx = p.origin[0], sy = p.origin[1], sz = p.origin[2];
   const float origin_x = static_cast<float>(g.pos[0]) + nrows * resolution * 0.5f;
@@ -223,156 +319,170 @@ raycast_scan_kernel(const __grid_constant__ RaycastParams p, const DeviceState* 
   const int r_s = static_cast<int>(floorf(gr0));  // the sensor's cell: every ray starts here
   const int c_s = static_cast<int>(floorf(gc0));
   const int win_r0 = r_s - kNearHalf, win_c0 = c_s - kNearHalf;
-  const int start_r = g.start[0], start_c = g.start[1];
   const int max_steps = nrows + ncols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* __restrict__ far_x = p.ray_min_enc;
+  // float32 start cell inside the map (the precondition tests the origin in float64; the two
+  // can disagree by a rounding at the map's edge — those scans take the generic loop below)
+  const bool start_inside = static_cast<unsigned>(r_s) < static_cast<unsigned>(nrows) &&
+                            static_cast<unsigned>(c_s) < static_cast<unsigned>(ncols);
 
-  for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) near_min[h] = kEncInit;
+  for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) near_x[h] = 0u;
   __syncthreads();
 
-  for (uint32_t base = blockIdx.x * kBlock; base < n_max; base += gridDim.x * kBlock) {
-    if (rkeys[base] == kRayInvalid) break;  // sorted, untraced entries last: nothing left
-    const uint32_t i = base + threadIdx.x;
-    if (i >= n_max || rkeys[i] == kRayInvalid) continue;
-    const float4 pt = __ldg(&pts[rvals[i]]);
+  const uint32_t n_tasks = (n_rays + 31u) >> 5;
+  for (uint32_t task = warp * gridDim.x + blockIdx.x; task < n_tasks; task += (kBlock / 32) * gridDim.x) {
+    const uint32_t i = task * 32u + lane;
+    bool alive = i < n_rays;
+    const float4 pt = alive ? __ldg(&rays[i]) : make_float4(sx, sy, sz, 0.0f);
     const float dz = pt.z - sz;
     const float gr1 = (origin_x - pt.x) / resolution;
     const float gc1 = (origin_y - pt.y) / resolution;
     const float dr = gr1 - gr0;
     const float dc = gc1 - gc0;
-    int r = r_s;
-    int c = c_s;
+    int r = r_s, c = c_s;
     int step_r, step_c;
-    float t_max_r, t_max_c, t_delta_r, t_delta_c;
+    float t_r, t_c, td_r, td_c;  // t_max_r / t_max_c / t_delta_r / t_delta_c
     if (fabsf(dr) > 1e-8f) {
       step_r = (dr > 0) ? 1 : -1;
       const float boundary = (step_r > 0) ? (r + 1.0f) : static_cast<float>(r);
-      t_max_r = (boundary - gr0) / dr;
-      t_delta_r = static_cast<float>(step_r) / dr;
+      t_r = (boundary - gr0) / dr;
+      td_r = static_cast<float>(step_r) / dr;
     } else {
       step_r = 0;
-      t_max_r = 1e30f;
-      t_delta_r = 1e30f;
+      t_r = 1e30f;
+      td_r = 1e30f;
     }
     if (fabsf(dc) > 1e-8f) {
       step_c = (dc > 0) ? 1 : -1;
       const float boundary = (step_c > 0) ? (c + 1.0f) : static_cast<float>(c);
-      t_max_c = (boundary - gc0) / dc;
-      t_delta_c = static_cast<float>(step_c) / dc;
+      t_c = (boundary - gc0) / dc;
+      td_c = static_cast<float>(step_c) / dc;
     } else {
       step_c = 0;
-      t_max_c = 1e30f;
-      t_delta_c = 1e30f;
+      t_c = 1e30f;
+      td_c = 1e30f;
     }
-    // The sensor cell is inside the map (precondition) and the map is convex, so once a ray
-    // has left the map it never comes back: the reference keeps stepping (its cells fail the
-    // bounds test and are ignored); stopping there changes nothing but the work.
-    bool was_inside = false;
-    bool done = false;
-    int s = 0;
 
-    // ── near field: shared-memory window ──
-    while (!done && s < max_steps) {
+    if (!start_inside) {
+      // generic traversal, one cell per round trip, every test of the reference's loop.  The map
+      // is convex: once a ray has left it, it never comes back (the reference keeps stepping
+      // through cells that fail its bounds test; stopping there changes nothing).
+      bool was_inside = false;
+      for (int s = 0; alive && s < max_steps; ++s) {
+        const bool row = t_r < t_c;
+        const float t_exit = row ? t_r : t_c;   // == min(t_max_r, t_max_c)
+        if (static_cast<unsigned>(r) < static_cast<unsigned>(nrows) &&
+            static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
+          was_inside = true;
+          atomicMax(&far_x[c * nrows + r], __float_as_uint(fminf(t_exit, 1.0f) * dz));
+        } else if (was_inside) {
+          break;
+        }
+        if (t_exit >= 1.0f) break;
+        if (row) { r += step_r; t_r += td_r; } else { c += step_c; t_c += td_c; }
+      }
+      continue;
+    }
+    // Start cell inside the map: every cell reached before the ray steps onto row r_out or
+    // column c_out is inside, so the bounds test is two compares after each step and the
+    // reference's step cap (nrows + ncols) can never bind first.
+    const int r_out = step_r > 0 ? nrows : -1;      // step_r == 0: r never changes, never equal
+    const int c_out = step_c > 0 ? ncols : -1;
+    const int dlin_c = step_c * nrows;
+    int lin = c * nrows + r;
+
+    // ── near field: shared-memory window around the sensor ──
+    while (alive) {
       const int wr = r - win_r0, wc = c - win_c0;
       if (static_cast<unsigned>(wr) >= static_cast<unsigned>(kNear) ||
           static_cast<unsigned>(wc) >= static_cast<unsigned>(kNear))
         break;  // left the window: continue in the far field
-      if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
-        was_inside = true;
-        const float t_exit = fminf(t_max_r, t_max_c);
-        const uint32_t e = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
-        uint32_t* slot = &near_min[wc * kNear + wr];
-        // a minimum only decreases: a value read without the atomic can only be too LARGE,
-        // so the atomic may be issued needlessly but is never skipped wrongly
-        if (e < *slot) atomicMin(slot, e);
-      } else if (was_inside) {
-        done = true;
-        break;
-      }
-      if (t_max_r < t_max_c) {
-        if (t_max_r >= 1.0f) done = true;
-        else { r += step_r; t_max_r += t_delta_r; }
-      } else {
-        if (t_max_c >= 1.0f) done = true;
-        else { c += step_c; t_max_c += t_delta_c; }
-      }
-      ++s;
+      const bool row = t_r < t_c;
+      const float t_exit = row ? t_r : t_c;
+      const uint32_t e = __float_as_uint(fminf(t_exit, 1.0f) * dz);
+      uint32_t* slot = &near_x[wc * kNear + wr];
+      if (e > *slot) atomicMax(slot, e);
+      if (t_exit >= 1.0f) { alive = false; break; }
+      if (row) { r += step_r; t_r += td_r; lin += step_r; } else { c += step_c; t_c += td_c; lin += dlin_c; }
+      alive = r != r_out && c != c_out;
     }
 
     // ── far field: global scratch, kRayBatch cells per memory round trip ──
-    while (!done) {
-      uint32_t* sl[kRayBatch];
+    while (__any_sync(0xffffffffu, alive)) {
+      int idx[kRayBatch];
       uint32_t ev[kRayBatch];
       uint32_t cv[kRayBatch];
 #pragma unroll
       for (int k = 0; k < kRayBatch; ++k) {
-        sl[k] = nullptr;
-        ev[k] = 0u;
-        if (done) continue;
-        if (s >= max_steps) { done = true; continue; }
-        if (r >= 0 && r < nrows && c >= 0 && c < ncols) {
-          was_inside = true;
-          int mr = r + start_r;  // == (r + start) % size: both terms are in [0, size)
-          if (mr >= nrows) mr -= nrows;
-          int mc = c + start_c;
-          if (mc >= ncols) mc -= ncols;
-          sl[k] = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
-          const float t_exit = fminf(t_max_r, t_max_c);
-          ev[k] = enc_f32(sz + fminf(t_exit, 1.0f) * dz);
-        } else if (was_inside) {
-          done = true;
-          continue;
-        }
-        if (t_max_r < t_max_c) {
-          if (t_max_r >= 1.0f) done = true;
-          else { r += step_r; t_max_r += t_delta_r; }
-        } else {
-          if (t_max_c >= 1.0f) done = true;
-          else { c += step_c; t_max_c += t_delta_c; }
-        }
-        ++s;
+        const bool row = t_r < t_c;
+        const float t_exit = row ? t_r : t_c;
+        ev[k] = __float_as_uint(fminf(t_exit, 1.0f) * dz);
+        idx[k] = alive ? lin : -1;
+        r += row ? step_r : 0;
+        c += row ? 0 : step_c;
+        lin += row ? step_r : dlin_c;
+        t_r = row ? t_r + td_r : t_r;
+        t_c = row ? t_c : t_c + td_c;
+        // the ray ended in that cell (t >= 1), or has just stepped out of the map
+        alive = alive && t_exit < 1.0f && r != r_out && c != c_out;
       }
-      // plain (L1-cacheable) loads: staleness is safe for the same reason as above
 #pragma unroll
-      for (int k = 0; k < kRayBatch; ++k) cv[k] = sl[k] ? *sl[k] : 0u;
+      for (int k = 0; k < kRayBatch; ++k) cv[k] = idx[k] >= 0 ? far_x[idx[k]] : 0xffffffffu;
 #pragma unroll
-      for (int k = 0; k < kRayBatch; ++k)
-        if (sl[k] && ev[k] < cv[k]) atomicMin(sl[k], ev[k]);
+      for (int k = 0; k < kRayBatch; ++k) {
+        const bool want = ev[k] > cv[k];
+        if (__any_sync(0xffffffffu, want)) {  // warp-uniform: every lane takes part in the election
+          // lanes that lower the same cell elect the one with the lowest ray (lowest lane on a
+          // tie); lanes with nothing to write get a key of their own
+          const uint32_t peers = __match_any_sync(0xffffffffu, want ? idx[k] : -(lane + 2));
+          const uint32_t best = __reduce_max_sync(peers, want ? ev[k] : 0u);
+          const uint32_t winners = __ballot_sync(0xffffffffu, want && ev[k] == best);
+          if (want && ev[k] == best && (__ffs(winners & peers) - 1) == lane) atomicMax(&far_x[idx[k]], best);
+        }
+      }
     }
   }
 
   // ── flush the window: every near-field cell this CTA lowered, once ──
   __syncthreads();
   for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) {
-    const uint32_t v = near_min[h];
-    if (v == kEncInit) continue;
+    const uint32_t v = near_x[h];
+    if (v == 0u) continue;
     const int r = win_r0 + (h % kNear), c = win_c0 + (h / kNear);  // in the map: only such cells are written
-    int mr = r + start_r;
-    if (mr >= nrows) mr -= nrows;
-    int mc = c + start_c;
-    if (mc >= ncols) mc -= ncols;
-    uint32_t* slot = &p.ray_min_enc[static_cast<size_t>(mc) * nrows + mr];
-    if (v < __ldcg(slot)) atomicMin(slot, v);
+    uint32_t* slot = &far_x[c * nrows + r];
+    if (v > __ldcg(slot)) atomicMax(slot, v);
   }
 }
 
 // map.clear(raycasting) (:242) + the observed log-odds updates + resolveGhostCells
-// (:188-214), one thread per cell; also rearms the scratch for the next scan.
+// (:188-214), one thread per cell; also rearms the scratch for the next scan.  `hits` is
+// indexed like the layers (buffer cell), the ray minima by LOGICAL cell (see the DDA kernel).
 __global__ void __launch_bounds__(kBlock)
-raycast_resolve_kernel(const __grid_constant__ RaycastParams p,
+raycast_resolve_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
                        const __grid_constant__ LayerTable lt,
                        const uint32_t* __restrict__ counters, size_t n_cells) {
   if (counters[CNT_RC_SKIP]) return;  // applyRaycasting returned before touching anything
+  const int nrows = st->geom.rows, ncols = st->geom.cols;
+  const int start_r = st->geom.start[0], start_c = st->geom.start[1];
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n_cells; i += stride) {
+    const int bc = static_cast<int>(i / static_cast<size_t>(nrows));
+    const int br = static_cast<int>(i - static_cast<size_t>(bc) * nrows);
+    int lr = br - start_r;  // buffer = (logical + start) % size
+    if (lr < 0) lr += nrows;
+    int lc = bc - start_c;
+    if (lc < 0) lc += ncols;
+    uint32_t* enc_slot = &p.ray_min_enc[static_cast<size_t>(lc) * nrows + lr];
     const uint32_t hits = p.hits[i];
-    const uint32_t enc = p.ray_min_enc[i];
-    if (hits == 0 && enc == kEncInit) {
+    const uint32_t enc = *enc_slot;
+    if (hits == 0 && enc == 0u) {
       p.raycasting[i] = nanf_();
       continue;
     }
     p.hits[i] = 0;
-    p.ray_min_enc[i] = kEncInit;
+    *enc_slot = 0u;
     float lo = p.logodds[i];
     bool lo_dirty = false;
     if (hits) {
@@ -386,8 +496,8 @@ raycast_resolve_kernel(const __grid_constant__ RaycastParams p,
     }
     float rmin = nanf_();
     bool cleared = false;
-    if (enc != kEncInit) {
-      rmin = dec_f32(enc);
+    if (enc != 0u) {
+      rmin = p.origin[2] + __uint_as_float(enc);  // start.z() + min(t_exit, 1) * dz of the lowest ray
       const float elev = p.elevation[i];
       if (!isnan(elev) && elev > rmin + p.height_conflict_threshold) {
         if (isnan(lo)) lo = 0.0f;
@@ -963,18 +1073,38 @@ void launch_voxel_select32(const uint32_t* sorted_keys, const uint32_t* sorted_v
       sorted_keys, sorted_vals, n, invalid_key, counters, out_sel);
   ++lc.mine;
 }
-int ray_key_bits() { return kRayKeyBits; }
-void launch_ray_keys(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                     const uint32_t* sel, uint32_t n_max, uint32_t* counters, uint32_t* rkeys,
-                     uint32_t* rvals, cudaStream_t s, LaunchCounter& lc) {
-  if (n_max == 0) return;
-  ray_keys_kernel<<<(n_max + kBlock - 1) / kBlock, kBlock, 0, s>>>(p, st, pts, sel, n_max, counters,
-                                                                  rkeys, rvals);
-  ++lc.mine;
+size_t ray_sort_scratch_words() { return 2 * static_cast<size_t>(kRayBins); }
+
+static void launch_ray_bundle_sort(const RaySortScratch& rs, uint32_t n_max, const uint32_t* counters,
+                                   cudaStream_t s, LaunchCounter& lc) {
+  ray_bin_scan_kernel<<<1, 1024, 0, s>>>(rs.hist, rs.hist + kRayBins);
+  const uint32_t want = (n_max + kBlock - 1) / kBlock;
+  ray_bin_scatter_kernel<<<want < 148u * 4u ? want : 148u * 4u, kBlock, 0, s>>>(rs.unsorted, rs.rays,
+                                                                              rs.hist + kRayBins, counters);
+  lc.mine += 2;
 }
-void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const float4* pts,
-                         const uint32_t* rkeys, const uint32_t* rvals, uint32_t n_max,
-                         cudaStream_t s, LaunchCounter& lc) {
+void launch_voxel_select_rays32(const uint32_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                                uint32_t invalid_key, const RaycastParams& p, const DeviceState* st,
+                                const float4* pts, uint32_t* counters, const RaySortScratch& rs,
+                                cudaStream_t s, LaunchCounter& lc) {
+  if (n == 0) return;
+  voxel_select_rays_kernel<uint32_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(
+      sorted_keys, sorted_vals, n, invalid_key, p, st, pts, counters, rs.unsorted, rs.hist);
+  ++lc.mine;
+  launch_ray_bundle_sort(rs, n, counters, s, lc);
+}
+void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sorted_vals, uint32_t n,
+                                const RaycastParams& p, const DeviceState* st, const float4* pts,
+                                uint32_t* counters, const RaySortScratch& rs, cudaStream_t s,
+                                LaunchCounter& lc) {
+  if (n == 0) return;
+  voxel_select_rays_kernel<uint64_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(
+      sorted_keys, sorted_vals, n, kInvalidVoxel, p, st, pts, counters, rs.unsorted, rs.hist);
+  ++lc.mine;
+  launch_ray_bundle_sort(rs, n, counters, s, lc);
+}
+void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
+                        uint32_t n_max, const uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
   if (n_max == 0) return;
   // near-field window size / persistent CTAs per SM (FDEM_RAY_NEAR=64|96|128 overrides)
   static int near = -1;
@@ -983,23 +1113,24 @@ void launch_raycast_scan(const RaycastParams& p, const DeviceState* st, const fl
     near = e ? std::atoi(e) : 96;
     if (near != 64 && near != 96 && near != 128) near = 96;
   }
-  const uint32_t chunks = (n_max + kBlock - 1) / kBlock;
+  const uint32_t chunks = (n_max + 31) / 32;  // warps fetch 32 rays at a time
   auto launch = [&](auto kernel, int kn, uint32_t ctas_per_sm) {
     const size_t smem = sizeof(uint32_t) * kn * kn;
     // opt-in to > 48 KiB of dynamic shared memory (per device, so not cached in a static)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    const uint32_t grid = chunks < 148u * ctas_per_sm ? chunks : 148u * ctas_per_sm;
-    kernel<<<grid, kBlock, smem, s>>>(p, st, pts, rkeys, rvals, n_max);
+    const uint32_t want = (chunks + (kBlock / 32) - 1) / (kBlock / 32);
+    const uint32_t grid = want < 148u * ctas_per_sm ? want : 148u * ctas_per_sm;
+    kernel<<<grid, kBlock, smem, s>>>(p, st, rays, counters);
   };
-  if (near == 64) launch(raycast_scan_kernel<64>, 64, 8u);
-  else if (near == 96) launch(raycast_scan_kernel<96>, 96, 5u);
-  else launch(raycast_scan_kernel<128>, 128, 3u);
+  if (near == 64) launch(raycast_dda_kernel<64>, 64, 8u);
+  else if (near == 96) launch(raycast_dda_kernel<96>, 96, 5u);
+  else launch(raycast_dda_kernel<128>, 128, 3u);
   ++lc.mine;
 }
-void launch_raycast_resolve(const RaycastParams& p, const DeviceState* /*st*/,
+void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st,
                             const LayerTable& lt, const uint32_t* counters, size_t n_cells,
                             cudaStream_t s, LaunchCounter& lc) {
-  raycast_resolve_kernel<<<grid_for(n_cells, kBlock), kBlock, 0, s>>>(p, lt, counters, n_cells);
+  raycast_resolve_kernel<<<grid_for(n_cells, kBlock), kBlock, 0, s>>>(p, st, lt, counters, n_cells);
   ++lc.mine;
 }
 int launch_median_filter(const float* src, float* dst, const DeviceState* st, int kernel_size,

@@ -99,16 +99,21 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
     const float4 q = __ldg(&p.pm[i]);
     const bool has_i = p.intensity != nullptr;
     const float in = has_i ? __ldg(&p.intensity[i]) : 0.0f;
-    if (key != INV) v = obs_from_point(q.z, q.w, in, has_i, i);
+    if (key != INV) v = obs_from_point(q.z, q.w, in, has_i, i + p.index_base);
   }
   // updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146) restricted to the cells
-  // that can hold a value: those the last observing scan touched.  Runs only when this scan
-  // has observations (update() returns early otherwise, :116-117); K3t writes this scan's
-  // values afterwards.
+  // that can hold a value: those the last observing scan touched (the whole layer when the
+  // caller edited it, SF_OBSTACLE_DIRTY).  Runs only when this scan has observations (update()
+  // returns early otherwise, :116-117); K3t writes this scan's values afterwards.
   if (n_inside > 0 && p.obstacle) {
-    for (uint32_t j = i; j < n_prev; j += gridDim.x * blockDim.x) {
-      const uint32_t k = p.touched_keys[j];
-      if (k != INV) p.obstacle[k] = nan_f32();
+    const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+    if (p.st_cur->flags & SF_OBSTACLE_DIRTY) {
+      for (size_t c = i; c < p.obstacle_cells; c += nthreads) p.obstacle[c] = nan_f32();
+    } else {
+      for (size_t j = i; j < n_prev; j += nthreads) {
+        const uint32_t k = p.touched_keys[j];
+        if (k != INV) p.obstacle[k] = nan_f32();
+      }
     }
   }
   // runs of consecutive lanes that hit the same cell
@@ -141,10 +146,11 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   }
 }
 
-// phase timeline of CTA 0's first bucket (SM clock ticks since kernel entry), for tuning:
-// read back through fdem_mapper_debug_phase_clocks().  One thread, a dozen clock reads.
+// Tuning probes, compiled only with -DFDEM_PROBES (tools/phase_probe.py): phase timeline of
+// CTA 0's first bucket (SM clock ticks since kernel entry) and the wall-clock entry / exit of
+// every CTA of the last launch.  The production build carries none of this.
+#ifdef FDEM_PROBES
 __device__ long long g_k3t_clocks[16];
-// wall-clock (globaltimer, ns) entry / exit of every CTA of the last launch (first 512 CTAs)
 __device__ unsigned long long g_k3t_cta_ns[2 * 512];
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -152,6 +158,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 #define K3T_MARK(i) do { if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[i] = clock64() - t_entry; } while (0)
+#else
+#define K3T_MARK(i) do { } while (0)
+#endif
 
 // ───────────────────────────── L2: per-bucket sort + reduce + estimate ───────
 // Compiled for three bucket shapes; the mapper picks one per scan (capi.cu):
@@ -211,11 +220,43 @@ __device__ __forceinline__ void acc_store(S_& S, uint32_t a, const CellObs& t) {
   S.a_it[a] = t.it; S.a_fi[a] = t.fi; S.a_li[a] = t.li;
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(TileCfg<BITS>::kThr, TileCfg<BITS>::kMinBlocks)
-tile_estimate_kernel(const __grid_constant__ EstimateParams p,
-                     const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters,
-                     DeviceState* __restrict__ st_out, const __grid_constant__ PublishArgs pub) {
+// system-scope flag traffic of the multi-GPU handshake (flags live in peer-mapped memory)
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// stage records [cs, cs + cn) of a sharded bucket — the concatenation of its pieces in the
+// sources' record buffers (peer memory, read over NVLink by the TMA engine) — one bulk copy per
+// piece that overlaps the chunk
+__device__ __forceinline__ void tma_load_pieces(CellRecord* stage, const ShardJob& J, const ShardBackArgs& sh,
+                                                uint32_t cs, uint32_t cn, uint64_t* bar) {
+  uint32_t pos = 0;
+  for (int s = 0; s < sh.world; ++s) {
+    const uint32_t lo = max(cs, pos), hi = min(cs + cn, pos + J.cnt[s]);
+    if (lo < hi)
+      tma_load_1d(stage + (lo - cs), sh.peer_records[s] + J.off[s] + (lo - pos),
+                  (hi - lo) * static_cast<uint32_t>(sizeof(CellRecord)), bar);
+    pos += J.cnt[s];
+  }
+}
+
+// SHARD = false: one GPU, jobs = the bucket list K2 wrote, records in this GPU's scratch.
+// SHARD = true: multi-GPU GLOBAL map, back half: jobs = the ShardJob list shard_gather_kernel
+// built for this rank's stripe, records pulled from every source rank's arena.
+template <int BITS, bool SHARD>
+__device__ __forceinline__ void
+tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __restrict__ counters,
+                   DeviceState* __restrict__ st_out, const PublishArgs& pub, const ShardBackArgs* shp) {
   using C = TileCfg<BITS>;
   constexpr int kThr = C::kThr;
   constexpr int kCells = C::kCells;
@@ -226,9 +267,11 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+#ifdef FDEM_PROBES
   const long long t_entry = clock64();
   bool first_job = true;
   if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x] = globaltimer_ns();
+#endif
 
   // batched graphs: the next scan's back prologue may launch now and wait for this grid to finish
   pdl_launch_dependents();
@@ -243,28 +286,45 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   // (the list has one slot per bucket and the grid never exceeds that, so the speculative
   // read is in bounds; it is used only when job < n_jobs, i.e. when this scan wrote it)
   const uint32_t n_jobs = counters[CNT_BUCKETS];
-  uint4 entry_next = tb.bucket_list[blockIdx.x];
+  uint4 entry_next = make_uint4(0u, 0u, 0u, 0u);
+  if (!SHARD) entry_next = tb.bucket_list[blockIdx.x];
 
   // static round-robin over the non-empty buckets K2 listed: no work-fetch atomics
   for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
     __syncthreads();  // previous bucket completely done (also publishes the mbarrier init)
-    const uint4 entry = entry_next;  // {bucket, first record slot, points, -}
-    if (job + gridDim.x < n_jobs) entry_next = tb.bucket_list[job + gridDim.x];  // prefetch
-    const uint32_t b = entry.x;
-    const uint32_t off = entry.y;
-    // Stage the first chunk right away.  The record count is not known yet (it is being
-    // loaded below); the bucket's POINT count bounds it and the segment has that many
-    // slots, so copying min(points, chunk) records is in bounds and always enough.
-    const uint32_t first_n = min(entry.z, static_cast<uint32_t>(kChunk));
-    if (tid == 0) {
-      fence_proxy_async();  // earlier generic-proxy reads of `stage` precede the async write
-      mbar_expect_tx(&S.mbar, first_n * static_cast<uint32_t>(sizeof(CellRecord)));
-      tma_load_1d(S.stage, tb.records + off, first_n * static_cast<uint32_t>(sizeof(CellRecord)),
-                  &S.mbar);
+    uint32_t b, off = 0, nrec;
+    ShardJob J;
+    if (SHARD) {
+      J = shp->jobs[job];  // {bucket, records, per-source (first slot, count)}
+      b = J.bucket;
+      nrec = J.total;
+      if (tid == 0) {
+        const uint32_t first_n = min(nrec, static_cast<uint32_t>(kChunk));
+        fence_proxy_async();
+        mbar_expect_tx(&S.mbar, first_n * static_cast<uint32_t>(sizeof(CellRecord)));
+        tma_load_pieces(S.stage, J, *shp, 0u, first_n, &S.mbar);
+      }
+    } else {
+      const uint4 entry = entry_next;  // {bucket, first record slot, points, -}
+      if (job + gridDim.x < n_jobs) entry_next = tb.bucket_list[job + gridDim.x];  // prefetch
+      b = entry.x;
+      off = entry.y;
+      // Stage the first chunk right away.  The record count is not known yet (it is being
+      // loaded below); the bucket's POINT count bounds it and the segment has that many
+      // slots, so copying min(points, chunk) records is in bounds and always enough.
+      const uint32_t first_n = min(entry.z, static_cast<uint32_t>(kChunk));
+      if (tid == 0) {
+        fence_proxy_async();  // earlier generic-proxy reads of `stage` precede the async write
+        mbar_expect_tx(&S.mbar, first_n * static_cast<uint32_t>(sizeof(CellRecord)));
+        tma_load_1d(S.stage, tb.records + off, first_n * static_cast<uint32_t>(sizeof(CellRecord)),
+                    &S.mbar);
+      }
+      nrec = tb.bucket_cursor[b];  // in flight together with the bulk copy
     }
-    const uint32_t nrec = tb.bucket_cursor[b];  // in flight together with the bulk copy
     K3T_MARK(1);  // job entry + record count loaded
+#ifdef FDEM_PROBES
     if (blockIdx.x == 0 && tid == 0 && first_job) g_k3t_clocks[15] = nrec;
+#endif
     // single-chunk bucket: cells are reduced from scratch straight into the touched list;
     // multi-chunk bucket: per-cell accumulators carry a cell across chunks
     const bool single = nrec <= static_cast<uint32_t>(kChunk);
@@ -279,8 +339,9 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
         if (tid == 0) {
           fence_proxy_async();
           mbar_expect_tx(&S.mbar, cn * static_cast<uint32_t>(sizeof(CellRecord)));
-          tma_load_1d(S.stage, tb.records + off + cs,
-                      cn * static_cast<uint32_t>(sizeof(CellRecord)), &S.mbar);
+          if (SHARD) tma_load_pieces(S.stage, J, *shp, cs, cn, &S.mbar);
+          else tma_load_1d(S.stage, tb.records + off + cs,
+                           cn * static_cast<uint32_t>(sizeof(CellRecord)), &S.mbar);
         }
         for (int c = tid; c < kCells; c += kThr) S.binoff[c] = 0;
       }
@@ -420,8 +481,10 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       // the atomic's round trip does not sit in front of a cell's loads.
       S.list_base = nt ? atomicAdd(&st_out->touched_count, nt) : 0u;
       if (nt) atomicAdd(&counters[CNT_CELLS], nt);
-      tb.bucket_count[b] = 0;   // re-arm the L1 scratch for the next scan
-      tb.bucket_cursor[b] = 0;
+      if (!SHARD) {             // (sharded: the source re-arms its own tables, shard_begin_kernel)
+        tb.bucket_count[b] = 0;   // re-arm the L1 scratch for the next scan
+        tb.bucket_cursor[b] = 0;
+      }
     }
 
     // ── estimator: one Kalman / P2 step per touched cell; each layer value is loaded once
@@ -441,7 +504,9 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
       if (p.touched_minz) p.touched_minz[lb + t] = S.a_mz[single ? t : c];
     }
     K3T_MARK(8);  // touched list written
+#ifdef FDEM_PROBES
     first_job = false;
+#endif
     if (job + gridDim.x < n_jobs) {
       // another bucket follows on this CTA: re-arm the bins
       __syncthreads();
@@ -453,7 +518,9 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
   // ── end of scan: the LAST CTA to finish publishes (no extra kernel / memset / memcpy):
   // scan statistics + committed state go to the host through mapped pinned memory, the
   // committed state becomes current, and the counters are re-armed for the next scan ──
+#ifdef FDEM_PROBES
   first_job = true;
+#endif
   K3T_MARK(9);  // all jobs of CTA 0 done
   if (pub.enabled) {
     __syncthreads();
@@ -479,10 +546,147 @@ tile_estimate_kernel(const __grid_constant__ EstimateParams p,
         pub.host_out[CNT_COUNT + lane] = w;
         reinterpret_cast<uint32_t*>(pub.st_cur)[lane] = w;
       }
+      if (SHARD && lane < shp->world) {
+        // every record of this scan has been read: the sources may reuse the buffers
+        __threadfence_system();
+        st_release_sys(&shp->peer_hdr[lane]->consumed[shp->rank], shp->seq);
+      }
     }
   }
   K3T_MARK(10);  // kernel exit of CTA 0
+#ifdef FDEM_PROBES
   if (tid == 0 && blockIdx.x < 512) g_k3t_cta_ns[2 * blockIdx.x + 1] = globaltimer_ns();
+#endif
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(TileCfg<BITS>::kThr, TileCfg<BITS>::kMinBlocks)
+tile_estimate_kernel(const __grid_constant__ EstimateParams p,
+                     const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters,
+                     DeviceState* __restrict__ st_out, const __grid_constant__ PublishArgs pub) {
+  tile_estimate_body<BITS, false>(p, tb, counters, st_out, pub, nullptr);
+}
+
+__global__ void __launch_bounds__(TileCfg<10>::kThr, TileCfg<10>::kMinBlocks)
+tile_estimate_shard_kernel(const __grid_constant__ EstimateParams p,
+                           const __grid_constant__ ShardBackArgs sh, uint32_t* __restrict__ counters,
+                           DeviceState* __restrict__ st_out, const __grid_constant__ PublishArgs pub) {
+  const TileBuffers none{};
+  tile_estimate_body<10, true>(p, none, counters, st_out, pub, &sh);
+}
+
+// ───────────────────────────── multi-GPU GLOBAL map: the handshake kernels ─────────────
+// FRONT, first kernel of a scan on every rank: wait until every owner has finished reading the
+// buffers this scan is about to overwrite (scan seq - 2 used the same parity), then re-arm the
+// bucket tables and the scan counters.
+__global__ void __launch_bounds__(256)
+shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, uint32_t* __restrict__ zero_a,
+                   uint32_t* __restrict__ zero_b, size_t n_words, uint32_t* __restrict__ counters) {
+  if (threadIdx.x < world && seq > 2) {
+    while (ld_acquire_sys(&hdr->consumed[threadIdx.x]) + 2u < seq) __nanosleep(64);
+  }
+  __syncthreads();
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+    zero_a[i] = 0u;
+    zero_b[i] = 0u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < CNT_COUNT) counters[threadIdx.x] = 0u;
+}
+
+// FRONT: bucket segment allocation for every (stripe, bucket) of this rank's slice — the same
+// two-atomics-per-warp scheme as commit_move_clear_kernel's group A
+__global__ void __launch_bounds__(256)
+shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t b = tid; b - lane < tb.n_buckets; b += nthreads) {
+    const uint32_t cnt = b < tb.n_buckets ? tb.bucket_count[b] : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t slot0 = 0;
+    if (lane == 0 && total) slot0 = atomicAdd(&counters[CNT_REC_SLOTS], total);
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (cnt) tb.bucket_offset[b] = slot0 + incl - cnt;
+  }
+}
+
+// FRONT, last kernel: tell every owner that this rank's records of scan `seq` are in place
+// (kernel boundaries have made them visible device-wide; the flag is a system-scope release)
+__global__ void shard_publish_front_kernel(const __grid_constant__ ShardFrontArgs a,
+                                           const uint32_t* __restrict__ counters) {
+  const int d = threadIdx.x;
+  if (d >= a.world) return;
+  const uint32_t inside = counters[CNT_INSIDE];
+  a.peer_hdr[d]->inside[a.seq & 1u][a.rank] = inside;
+  __threadfence_system();
+  st_release_sys(&a.peer_hdr[d]->ready[a.rank], a.seq);
+}
+
+// BACK, first kernel on every rank: wait for every source's front half, then (a) list the
+// non-empty buckets of this rank's stripe with their record pieces, (b) do the map-side
+// bookkeeping the one-GPU pipeline does in K2 / scatter: the obstacle reset of the last observing
+// scan's cells, the touched-list hand-over and the sticky state flags — all decided on the
+// scan-wide observation count, as the reference's single map would.
+__global__ void __launch_bounds__(256)
+shard_gather_kernel(const __grid_constant__ ShardBackArgs a, uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_inside;
+  if (threadIdx.x < a.world)
+    while (ld_acquire_sys(&a.hdr->ready[threadIdx.x]) < a.seq) __nanosleep(64);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int s = 0; s < a.world; ++s) t += ld_relaxed_sys(&a.hdr->inside[a.seq & 1u][s]);
+    s_inside = t;
+  }
+  __syncthreads();
+  const uint32_t scan_inside = s_inside;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const uint32_t prev = a.st_cur->touched_count;
+  const uint32_t flags_in = a.st_cur->flags;
+  if (tid == 0) {
+    a.st_out->geom = a.st_cur->geom;  // GLOBAL maps never move
+    a.st_out->touched_count = scan_inside > 0 ? 0u : prev;
+    uint32_t flags = flags_in;
+    if (scan_inside > 0) flags = (flags | a.flags_if_cells) & ~static_cast<uint32_t>(SF_OBSTACLE_DIRTY);
+    a.st_out->flags = flags;
+  }
+  if (scan_inside > 0 && a.obstacle) {
+    if (flags_in & SF_OBSTACLE_DIRTY) {
+      for (size_t c = tid; c < a.obstacle_cells; c += nthreads) a.obstacle[c] = nan_f32();
+    } else {
+      for (size_t j = tid; j < prev; j += nthreads) {
+        const uint32_t k = a.touched_keys[j];
+        if (k != a.invalid_key) a.obstacle[k] = nan_f32();
+      }
+    }
+  }
+  // job list: one thread per bucket of the stripe, `world` remote 4-byte reads each (the counts
+  // were final before the ready flag was released)
+  const uint32_t g0 = static_cast<uint32_t>(a.rank) * a.bps;
+  for (size_t b = tid; b < a.bps; b += nthreads) {
+    ShardJob J;
+    J.bucket = static_cast<uint32_t>(b);
+    J.total = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxShards; ++s) {
+      J.cnt[s] = s < a.world ? ld_relaxed_sys(&a.peer_cursor[s][g0 + b]) : 0u;
+      J.off[s] = 0;
+      J.total += J.cnt[s];
+    }
+    if (J.total == 0) continue;
+#pragma unroll
+    for (int s = 0; s < kMaxShards; ++s)
+      if (J.cnt[s]) J.off[s] = ld_relaxed_sys(&a.peer_offset[s][g0 + b]);
+    a.jobs[atomicAdd(&counters[CNT_BUCKETS], 1u)] = J;
+  }
 }
 
 template <int BITS>
@@ -493,6 +697,7 @@ uint32_t tile_grid(uint32_t n_buckets) {
 
 }  // namespace
 
+#ifdef FDEM_PROBES
 int tile_estimate_debug_cta_ns(unsigned long long* out1024) {
   return static_cast<int>(cudaMemcpyFromSymbol(out1024, g_k3t_cta_ns, sizeof(unsigned long long) * 1024));
 }
@@ -500,6 +705,7 @@ int tile_estimate_debug_cta_ns(unsigned long long* out1024) {
 int tile_estimate_debug_clocks(long long* out16) {
   return static_cast<int>(cudaMemcpyFromSymbol(out16, g_k3t_clocks, sizeof(long long) * 16));
 }
+#endif
 
 int tile_estimate_configure() {
   cudaError_t e = cudaFuncSetAttribute(tile_estimate_kernel<8>,
@@ -509,6 +715,9 @@ int tile_estimate_configure() {
   e = cudaFuncSetAttribute(tile_estimate_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(sizeof(TileSmem<9>)));
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(tile_estimate_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(sizeof(TileSmem<10>)));
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel<10>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(sizeof(TileSmem<10>))));
@@ -517,6 +726,33 @@ int tile_estimate_configure() {
 void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc) {
   if (p.n == 0) return;
   scatter_records_kernel<<<(p.n + kThreads - 1) / kThreads, kThreads, 0, s>>>(p);
+  ++lc.mine;
+}
+
+void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, uint32_t* zero_a, uint32_t* zero_b,
+                        size_t n_words, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+  shard_begin_kernel<<<148, 256, 0, s>>>(hdr, seq, world, zero_a, zero_b, n_words, counters);
+  ++lc.mine;
+}
+void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+  shard_alloc_kernel<<<148, 256, 0, s>>>(tb, counters);
+  ++lc.mine;
+}
+void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
+                                LaunchCounter& lc) {
+  shard_publish_front_kernel<<<1, 32, 0, s>>>(a, counters);
+  ++lc.mine;
+}
+void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+  shard_gather_kernel<<<148, 256, 0, s>>>(a, counters);
+  ++lc.mine;
+}
+void launch_tile_estimate_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
+                                DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
+                                LaunchCounter& lc) {
+  const uint32_t cap = 148u * static_cast<uint32_t>(TileCfg<10>::kMinBlocks);
+  tile_estimate_shard_kernel<<<a.bps < cap ? a.bps : cap, TileCfg<10>::kThr, sizeof(TileSmem<10>), s>>>(
+      p, a, counters, st_out, pub);
   ++lc.mine;
 }
 

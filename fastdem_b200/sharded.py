@@ -241,6 +241,86 @@ class ShardedGlobalMap:
         return cur
 
 
+class ShardedMapper:
+    """fastdem::FastDEM on ONE GLOBAL map row-striped over the ranks — the path whose compute
+    scales with the rank count (fdem_shard_* in the C-ABI, protocol in csrc/device_types.h):
+
+      front half, every rank: preprocessScan + binning of its 1/world slice of the scan, read in
+        place from wherever the scan lives (normally the ingest rank's HBM, over NVLink), for
+        EVERY stripe; the pre-reduced records stay in the rank's own arena;
+      back half, every rank: for the non-empty buckets of its own stripe, pull the record pieces
+        from all ranks' arenas (TMA bulk reads of peer memory) and run the per-cell estimator.
+
+    Device-side ready / consumed flags order the halves across ranks; torch.distributed is used
+    ONCE, to exchange the CUDA IPC handles of the arenas.  Every rank must call integrate_async
+    for every scan, in the same order, with channels that address the WHOLE scan in memory it
+    can read (e.g. PeerScanRing.cloud)."""
+
+    def __init__(self, width: float, height: float, resolution: float, cfg, *, max_points: int,
+                 device: int = 0, stream: int = 0, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import api, capi
+        self._C, self._capi, self._api = C, capi, api
+        self.lib = capi.load_library()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if cfg.mode != capi.MODE_GLOBAL:
+            raise ValueError("row-stripe sharding is for GLOBAL mapping")
+        self.rows = grid_rows(width, resolution)
+        self.cols = grid_rows(height, resolution)
+        self.r0, self.r1 = stripe_bounds(self.rows, self.world, self.rank)
+        if not stream and torch.cuda.is_available():
+            # order the map's work on torch's current stream, so tensors produced on it (a scan
+            # copied or received there) are complete before K1 reads them
+            stream = torch.cuda.current_stream(device).cuda_stream
+        self.map = api.ElevationMap(width, height, resolution, "map", device=device, stream=stream,
+                                    row_stripe=(self.r0, self.r1))
+        self.dem = api.FastDEM(self.map, cfg)
+        self._h = C.c_void_p()
+        capi.check(self.lib.fdem_shard_create(self.dem._h, self.rank, self.world, int(max_points),
+                                              C.byref(self._h)))
+        h = capi.FdemIpcHandle()
+        capi.check(self.lib.fdem_shard_export(self._h, C.byref(h)))
+        handles = [bytes(h)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(h), group=group)
+        arr = (capi.FdemIpcHandle * self.world)(*[capi.FdemIpcHandle.from_buffer_copy(b) for b in handles])
+        capi.check(self.lib.fdem_shard_connect(self._h, C.cast(arr, C.c_void_p)))
+        self._keep = None
+
+    def integrate_async(self, cloud, T_base_sensor, T_world_base) -> None:
+        api = self._api
+        px, k1, n = api._ptr(cloud.xyzw, np.float32)
+        pi, k2, _ = api._ptr(cloud.intensity, np.float32)
+        pc, k3, _ = api._ptr(cloud.color, np.uint8)
+        a, b = api._iso(T_base_sensor), api._iso(T_world_base)
+        self._keep = (k1, k2, k3, a, b)
+        self._capi.check(self.lib.fdem_shard_integrate(self._h, px, pi, pc, n, a.p, b.p))
+
+    def wait(self):
+        st = self._capi.FdemScanStats()
+        self._capi.check(self.lib.fdem_shard_wait(self._h, self._C.byref(st)))
+        return st
+
+    def integrate(self, cloud, T_base_sensor, T_world_base):
+        self.integrate_async(cloud, T_base_sensor, T_world_base)
+        return self.wait()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.fdem_shard_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PeerScanRing:
     """A ring of scan slots in the INGEST rank's HBM that every rank reads in place.
 

@@ -45,8 +45,11 @@ class Workload:
     def points_per_scan(self) -> int:
         return self.beams * self.azimuths
 
-    def config(self) -> capi.FdemConfig:
-        c = capi.default_config()
+    def config(self, default=None) -> capi.FdemConfig:
+        """fastdem::Config for this workload.  `default` = the function that yields Config{}
+        (the library's by default; the CPU-only reference arm passes the oracle's so that it
+        never maps the CUDA library)."""
+        c = (default or capi.default_config)()
         for k, v in self.cfg_overrides.items():
             setattr(c, k, v)
         return c

@@ -125,6 +125,12 @@ int32_t fdem_abi_version(void);
 const char* fdem_last_error(void);
 const char* fdem_status_string(fdem_status s);
 void fdem_config_default(fdem_config* cfg); /* = fastdem::Config{} */
+/* detail::validate of the reference's YAML loader (fastdem/src/config_fastdem.cpp:128-260):
+ * FDEM_ERR_INVALID_ARGUMENT where the reference throws (kalman min_variance >= max_variance,
+ * unsorted P2 markers), values the reference warns about are clamped in place and counted in
+ * *n_clamped (may be NULL).  A Config struct handed straight to FastDEM(map, cfg) is NOT
+ * validated by the reference, and fdem_mapper_create does not validate it either. */
+fdem_status fdem_config_validate(fdem_config* cfg, int32_t* n_clamped);
 
 /* ── map: fastdem::ElevationMap  (fastdem/include/fastdem/elevation_map.hpp:65-177) ── */
 
@@ -139,7 +145,16 @@ fdem_status fdem_map_create(float width, float height, float resolution, int32_t
 fdem_status fdem_map_create_stripe(float width, float height, float resolution,
                                    int32_t row_begin, int32_t row_end, int32_t device,
                                    void* stream, fdem_map** out);
+/* Destroys the map.  FastDEM objects (fdem_mapper) still bound to it are detached first: their
+ * calls then fail with FDEM_ERR_INVALID_ARGUMENT, fdem_mapper_destroy stays valid. */
 fdem_status fdem_map_destroy(fdem_map* map);
+/* ElevationMap::setGeometry(width, height, resolution) on an existing map, IN PLACE
+ * (elevation_map.hpp:112-116: nanoGrid setGeometry + clearAll): every existing layer is resized
+ * and reset to NaN, position and start index return to 0.  The handle — and every fdem_mapper
+ * bound to it, like the reference's FastDEM holding an ElevationMap& — stays valid; this is
+ * what io::loadNpz does to the map it restores into (fastdem/src/io_npz.cpp:440-).  Not valid
+ * on a row stripe. */
+fdem_status fdem_map_set_geometry(fdem_map* map, float width, float height, float resolution);
 
 fdem_status fdem_map_get_geometry(fdem_map* map, fdem_geometry* out);
 /* GridMap::setPosition / setStartIndex (used by snapshot/load, elevation_map.hpp:166-167) */
@@ -367,6 +382,38 @@ fdem_status fdem_ipc_export(int32_t device, const void* ptr, size_t bytes, fdem_
 fdem_status fdem_ipc_import(int32_t device, const fdem_ipc_handle* h, void** ptr);
 fdem_status fdem_ipc_close(int32_t device, void* ptr);
 
+/* ── multi-GPU GLOBAL map with compute that scales ────────────────────────
+ * One logical map, row-striped over `world` ranks, one process per GPU.  The reference has no
+ * distributed code; this is the B200-side answer to BASELINE.json's config 5.  Each rank holds
+ * its stripe (fdem_map_create_stripe with the rows fastdem_b200/sharded.py's stripe_bounds gives
+ * it), a FastDEM on it (GLOBAL mode) and one fdem_shard: the exchange arena every other rank maps
+ * over CUDA IPC.  A scan is integrated in two halves per rank, on the map's stream:
+ *   front: preprocessScan + binning of this rank's 1/world slice of the scan's points (read in
+ *          place from wherever the scan lives — e.g. the ingest GPU's HBM, over NVLink) for
+ *          EVERY stripe; the pre-reduced records stay in this rank's arena;
+ *   back:  for every non-empty bucket of this rank's OWN stripe, pull its record pieces from all
+ *          ranks' arenas (TMA bulk reads of peer memory) and run the per-cell estimator.
+ * Device-side ready / consumed flags order the halves across ranks: no collective, no host round
+ * trip.  Results are identical to one unsharded map (tests/test_gpu_shard.py).
+ * Setup: create on every rank -> export -> exchange the handles out of band (e.g.
+ * torch.distributed.all_gather_object) -> connect. */
+typedef struct fdem_shard fdem_shard;
+fdem_status fdem_shard_create(fdem_mapper* mapper, int32_t rank, int32_t world, size_t max_points,
+                              fdem_shard** out);
+fdem_status fdem_shard_destroy(fdem_shard* shard);
+fdem_status fdem_shard_export(fdem_shard* shard, fdem_ipc_handle* out);
+/* handles[world], indexed by rank (handles[rank] is ignored) */
+fdem_status fdem_shard_connect(fdem_shard* shard, const fdem_ipc_handle* handles);
+/* FastDEM::integrate(cloud, T_base_sensor, T_world_base) on the striped map, asynchronous.
+ * EVERY rank calls it for every scan, in the same order, with the same scan: xyzw / intensity /
+ * rgb address the WHOLE scan (n points) in device memory this rank can read. */
+fdem_status fdem_shard_integrate(fdem_shard* shard, const float* xyzw, const float* intensity,
+                                 const uint8_t* rgb, size_t n, const double T_base_sensor[16],
+                                 const double T_world_base[16]);
+/* waits for this rank's queued scans; stats of the newest as THIS rank saw it: n_kept = kept
+ * points of its slice, n_cells = touched cells of its stripe (sum over ranks = scan totals) */
+fdem_status fdem_shard_wait(fdem_shard* shard, fdem_scan_stats* stats);
+
 /* ── instrumentation ──────────────────────────────────────────────────────── */
 /* pipeline stages of one scan, in stream order */
 enum {
@@ -389,12 +436,6 @@ fdem_status fdem_mapper_stage_times(fdem_mapper* m, double ms[FDEM_STAGE_COUNT],
  *   GLOBAL one CUB radix sort of the whole scan + warp-segmented reduce (kernels.cu) */
 enum { FDEM_CELL_SORT_TILE = 0, FDEM_CELL_SORT_GLOBAL = 1 };
 fdem_status fdem_mapper_set_cell_sort(fdem_mapper* m, int32_t mode);
-/* tuning aid: SM-clock timeline of CTA 0's first bucket in the last tile_estimate launch
- * (out16[0..10] = phase boundaries in clock ticks since kernel entry, out16[15] = records) */
-fdem_status fdem_mapper_debug_phase_clocks(fdem_mapper* m, int64_t out16[16]);
-/* tuning aid: globaltimer (ns) at entry / exit of the first 512 CTAs of the last tile_estimate
- * launch, interleaved: out[2*i] = entry, out[2*i+1] = exit */
-fdem_status fdem_mapper_debug_cta_times(fdem_mapper* m, uint64_t out1024[1024]);
 /* kernels launched through CUB (radix-sort passes) since the map was created */
 fdem_status fdem_mapper_library_launch_count(fdem_mapper* m, int64_t* launches);
 /* number of kernels THIS library launched since the handle was created (bench.py's

@@ -34,9 +34,14 @@ def compare_layer(name, got, want, rtol=RTOL, atol=ATOL):
 
 
 def compare_maps(gpu_map, omap, layers=None, rtol=RTOL, atol=ATOL):
-    """Every layer the oracle holds must exist on the GPU map and match.  Returns
-    {layer: n_cells_with_different_bits}."""
+    """The two maps must hold exactly the same layer SET (the reference creates intensity /
+    color / the raycasting layers lazily, and exists() / getLayers() are part of its API) and
+    every layer must match.  Returns {layer: n_cells_with_different_bits}."""
     names = layers if layers is not None else omap.layers()
+    if layers is None:
+        assert sorted(gpu_map.getLayers()) == sorted(omap.layers()), (
+            f"layer sets differ: GPU-only {sorted(set(gpu_map.getLayers()) - set(omap.layers()))}, "
+            f"oracle-only {sorted(set(omap.layers()) - set(gpu_map.getLayers()))}")
     report = {}
     for name in names:
         assert gpu_map.exists(name), f"GPU map lacks layer {name}"

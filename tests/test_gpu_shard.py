@@ -1,0 +1,134 @@
+"""-m gpu: the compute-scaling multi-GPU path (fdem_shard_*, fastdem_b200.sharded.ShardedMapper).
+
+Every rank bins its 1/world slice of the scan for every stripe, owners pull their buckets'
+record pieces from all ranks' arenas, device-side flags order the halves.  Here: `world`
+PROCESSES on the one GPU of the test box (CUDA IPC mappings instead of NVLink peer mappings —
+the same code path); on a multi-GPU box the same worker runs one rank per GPU
+(tools/shard_parity.py under `gpurun --gpus N`).  The stripes must concatenate to the oracle's
+single map: every layer, the same layer set, the same cell counts."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from fastdem_b200 import capi, sharded
+from fastdem_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def run_rank(rank, world, port, out_dir, wl_name, n_scans, one_gpu=True, backend="gloo"):
+    """One rank of the sharded mapper: integrates n_scans scans of workload `wl_name` and saves
+    its stripe of every layer."""
+    import torch
+    import torch.distributed as dist
+    import fastdem_b200 as fd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = 0 if one_gpu else rank
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        wl = syn.WORKLOADS[wl_name]
+        cfg = wl.config()
+        cfg.mode = capi.MODE_GLOBAL
+        n = wl.points_per_scan
+        has_i, has_c = wl.has_intensity, wl.has_color
+        ring = sharded.PeerScanRing(3, n, has_i, has_c, device=dev, src=0)
+        sm = sharded.ShardedMapper(wl.map_width, wl.map_height, wl.resolution, cfg, max_points=n, device=dev)
+        cells = kept = 0
+        for k in range(n_scans):
+            s = syn.make_scan(wl, k)
+            if rank == 0:
+                ring.fill(k, s["xyzw"], s["intensity"], s["rgb"])
+                torch.cuda.synchronize()
+            dist.barrier()          # the slot is complete before any rank reads it
+            if k % 2 == 0:
+                st = sm.integrate(ring.cloud(k, n), s["T_base_sensor"], s["T_world_base"])
+            else:                   # queued: the next scan's front half follows without a host sync
+                sm.integrate_async(ring.cloud(k, n), s["T_base_sensor"], s["T_world_base"])
+                st = sm.wait()
+            cells += st.n_cells
+            kept += st.n_kept
+            dist.barrier()          # every rank is done with the slot before it is reused
+        out = {name: sm.map.get(name) for name in sm.map.getLayers()}
+        out["__cells"] = np.array([cells])
+        out["__kept"] = np.array([kept])
+        np.savez(os.path.join(out_dir, f"stripe{rank}.npz"), **out)
+        sm.close()
+        ring.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def check_against_oracle(out_dir, world, wl_name, n_scans):
+    parts = [np.load(os.path.join(out_dir, f"stripe{r}.npz")) for r in range(world)]
+    wl = syn.WORKLOADS[wl_name]
+    cfg = wl.config()
+    cfg.mode = capi.MODE_GLOBAL
+    om = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    od = ob.OracleFastDEM(om, cfg)
+    cells = kept = 0
+    for k in range(n_scans):
+        s = syn.make_scan(wl, k)
+        _, st, _ = od.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], s["rgb"])
+        cells += st.n_cells
+        kept += st.n_kept
+    assert sum(int(p["__cells"][0]) for p in parts) == cells
+    assert sum(int(p["__kept"][0]) for p in parts) == kept
+    names = sorted(k for k in parts[0].files if not k.startswith("__"))
+    for p in parts:
+        assert sorted(k for k in p.files if not k.startswith("__")) == names
+    assert names == sorted(om.layers()), (names, sorted(om.layers()))
+    bits_differ = 0
+    for name in names:
+        got = np.concatenate([p[name] for p in parts], axis=0)
+        want = om.get(name)
+        assert got.shape == want.shape, name
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        ok = ~np.isnan(want)
+        if name == "color":
+            assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32)), name
+        else:
+            assert np.allclose(got[ok], want[ok], rtol=1e-5, atol=1e-7), name
+        bits_differ += int(np.count_nonzero(got[ok].view(np.uint32) != want[ok].view(np.uint32)))
+    return bits_differ
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_mapper_matches_the_oracle(fdem, tmp_path, world):
+    import torch.multiprocessing as mp
+    mp.spawn(run_rank, args=(world, _free_port(), str(tmp_path), "tiny", 6), nprocs=world, join=True)
+    check_against_oracle(str(tmp_path), world, "tiny", 6)
+
+
+def test_sharded_mapper_world_1_equals_plain_mapper(fdem, tmp_path):
+    """Degenerate case in one process: the two-half pipeline against the one-GPU pipeline."""
+    wl = syn.WORKLOADS["c1_vlp16_local"]
+    cfg = wl.config()
+    cfg.mode = capi.MODE_GLOBAL
+    sm = sharded.ShardedMapper(wl.map_width, wl.map_height, wl.resolution, cfg, max_points=wl.points_per_scan)
+    m = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution, "map")
+    d = fdem.FastDEM(m, cfg)
+    for k in range(5):
+        s = syn.make_scan(wl, k)
+        import torch
+        cloud = fdem.PointCloud(torch.from_numpy(s["xyzw"]).cuda(), torch.from_numpy(s["intensity"]).cuda())
+        a = sm.integrate(cloud, s["T_base_sensor"], s["T_world_base"])
+        b = d.integrate_stats(cloud, s["T_base_sensor"], s["T_world_base"])
+        assert (a.n_kept, a.n_cells) == (b.n_kept, b.n_cells)
+    assert sm.map.getLayers() == m.getLayers()
+    for name in m.getLayers():
+        x, y = sm.map.get(name), m.get(name)
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), name
