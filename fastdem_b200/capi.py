@@ -132,6 +132,7 @@ SIGNATURES = {
     "fdem_raycast": (_ST, [_P, _f32p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(FdemConfig)]),
     "fdem_voxel_grid_any": (_ST, [_P, _f32p, C.c_size_t, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]),
     "fdem_inpaint": (_ST, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fdem_inpaint_stripe_sweep": (_ST, [_P, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "fdem_spatial_smoothing": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32]),
     "fdem_map_pack_pointcloud2": (_ST, [_P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),

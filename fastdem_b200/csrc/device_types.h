@@ -22,6 +22,7 @@ enum Counter : int {
   CNT_REC_SLOTS = 8,   // tile path: record slots handed out to bucket segments
   CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
   CNT_WORK = 10,       // tile path: K3t's dynamic work counter
+  CNT_RAY_WORK = 11,   // raycasting: next unfetched ray bundle
   CNT_COUNT = 12
 };
 
@@ -146,6 +147,7 @@ struct ShardBackArgs {               // owner side
   uint32_t invalid_key;
   uint32_t flags_if_cells;
   size_t obstacle_cells;
+  const uint32_t* front_counters;  // this rank's front-half counters of the scan (kept / inside of its slice)
 };
 
 // everything K1 needs for one scan (fastdem::Config + the two transforms, pre-cast on the
@@ -298,6 +300,10 @@ struct RaycastParams {
   float* ghost_removal;
   uint32_t* ray_min_enc;  // scratch, one u32 per LOGICAL cell: bits of the lowest ray's (height - sensor z) <= -0; 0 = none
   uint32_t* hits;         // scratch, one u32 per cell: observed-evidence hit counts
+  int32_t tune_ld_cg;     // far-field reads bypass L1 (always fresh) instead of L1-cached (maybe stale)
+  int32_t tune_elect;     // same-cell lanes of a bundle elect one atomic (1: match.any, 2: uniform-cell fast path)
+  int32_t seg_len;        // DDA steps per segment task
+  int32_t tune_az_mask;   // azimuth bins actually used for the ordering key (mask on the 1024-bin index)
 };
 
 // ── launchers (kernels.cu) ───────────────────────────────────────────────────
@@ -391,7 +397,7 @@ void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sor
                                 uint32_t* counters, const RaySortScratch& rs, cudaStream_t s,
                                 LaunchCounter& lc);
 void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
-                        uint32_t n_max, const uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+                        uint32_t n_max, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,
                             const uint32_t* counters, size_t n_cells, cudaStream_t s,
                             LaunchCounter& lc);
@@ -412,6 +418,8 @@ void launch_pack_pointcloud2(const float* elev, const float* const* fields, int 
                              const DeviceState* st, uint32_t* col_count, uint32_t* col_offset,
                              uint32_t* total, float* out, int phase, cudaStream_t s,
                              LaunchCounter& lc);
+void launch_inpaint_stripe(const float* src, float* dst, int rows_local, int cols, const float* above,
+                           const float* below, int min_valid, cudaStream_t s, LaunchCounter& lc);
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols);
 

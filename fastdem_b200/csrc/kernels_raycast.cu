@@ -203,10 +203,11 @@ voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restri
         float a = dy / l1;                        // [-1, 1]
         if (dx < 0.0f) a = 2.0f - a;              // (1, 3]
         else if (dy < 0.0f) a = 4.0f + a;         // [3, 4)
-        const int azbin = min(max(static_cast<int>(a * (kRayAzBins / 4)), 0), kRayAzBins - 1);
+        const int azbin = (min(max(static_cast<int>(a * (kRayAzBins / 4)), 0), kRayAzBins - 1)) & p.tune_az_mask;
         const uint32_t okey = static_cast<uint32_t>(lenbin * kRayAzBins + azbin);
         pt.w = __uint_as_float(okey);
         atomicAdd(&ray_hist[okey], 1u);
+        atomicAdd(&ray_hist[2 * kRayBins + lenbin], 1u);   // rays per length bin (segment bases)
       }
     }
   }
@@ -231,24 +232,25 @@ voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restri
   if (trace) rays_unsorted[s_base + s_warp[warp] + __popc(tm & ((1u << lane) - 1u))] = pt;
 }
 
-// counting sort of the ray list by ordering key, step 2 of 3: exclusive scan of the histogram
-// (one CTA; 32 K bins), cursors out, histogram re-armed for the next scan
-__global__ void __launch_bounds__(1024)
+// counting sort of the ray list by ordering key, step 2 of 3: one CTA per length bin — base of
+// the bin's segment from the per-length-bin totals, exclusive scan over its azimuth bins,
+// cursors out, histogram re-armed for the next scan
+__global__ void __launch_bounds__(kRayAzBins)
 ray_bin_scan_kernel(uint32_t* __restrict__ ray_hist, uint32_t* __restrict__ ray_cursor) {
-  __shared__ uint32_t s_warp[32];
-  constexpr int kPer = kRayBins / 1024;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t v[kPer];
-  uint32_t t = 0;
-  uint4* h4 = reinterpret_cast<uint4*>(ray_hist) + threadIdx.x * (kPer / 4);
+  __shared__ uint32_t s_warp[kRayAzBins / 32];
+  __shared__ uint32_t s_base;
+  const int L = blockIdx.x, t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const uint32_t* len_hist = ray_hist + 2 * kRayBins;
+  const uint32_t v = ray_hist[L * kRayAzBins + t];
+  ray_hist[L * kRayAzBins + t] = 0u;
+  if (warp == 0) {
+    uint32_t x = (lane < L) ? len_hist[lane] : 0u;   // kRayLenBins == 32: one lane per length bin
 #pragma unroll
-  for (int k = 0; k < kPer / 4; ++k) {
-    const uint4 q = h4[k];
-    v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-    t += q.x + q.y + q.z + q.w;
-    h4[k] = make_uint4(0u, 0u, 0u, 0u);
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) s_base = x;
   }
-  uint32_t inc = t;
+  uint32_t inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
@@ -258,12 +260,7 @@ ray_bin_scan_kernel(uint32_t* __restrict__ ray_hist, uint32_t* __restrict__ ray_
   __syncthreads();
   uint32_t wprefix = 0;
   for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
-  uint32_t base = wprefix + inc - t;
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    ray_cursor[threadIdx.x * kPer + k] = base;
-    base += v[k];
-  }
+  ray_cursor[L * kRayAzBins + t] = s_base + wprefix + inc - v;
 }
 
 // step 3 of 3: scatter (order inside a bin is irrelevant)
@@ -271,6 +268,8 @@ __global__ void __launch_bounds__(kBlock)
 ray_bin_scatter_kernel(const float4* __restrict__ rays_unsorted, float4* __restrict__ rays,
                        uint32_t* __restrict__ ray_cursor, const uint32_t* __restrict__ counters) {
   const uint32_t n_rays = counters[CNT_RAYS];
+  // the per-length-bin totals were consumed by the scan kernel: re-arm them
+  if (blockIdx.x == 0 && threadIdx.x < kRayLenBins) ray_cursor[kRayBins + threadIdx.x] = 0u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) {
     const float4 pt = rays_unsorted[i];
     rays[atomicAdd(&ray_cursor[__float_as_uint(pt.w)], 1u)] = pt;
@@ -300,10 +299,14 @@ constexpr int kRayBatch = 8;
 //    A stored value only moves one way, so a stale (L1-cached) read can at worst cause a
 //    needless atomic, never a missed one.  The lanes of a bundle often lower the same cell in
 //    the same step: they elect one atomic per cell (match.any + redux.max, warp-uniform).
-template <int kNear>
-__global__ void __launch_bounds__(kBlock)
+// x <= 0 in value, but a ray that leaves its first cell at t = -0 yields +0: force the sign bit so
+// that a visited cell never reads as 0 ("no ray"); fl(sz + -0) == fl(sz + +0) for any sz != -0
+__device__ __forceinline__ uint32_t enc_offset(float x) { return __float_as_uint(x) | 0x80000000u; }
+
+template <int kNear, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
 raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* __restrict__ st,
-                   const float4* __restrict__ rays, const uint32_t* __restrict__ counters) {
+                   const float4* __restrict__ rays, uint32_t* __restrict__ counters) {
   extern __shared__ uint32_t near_x[];  // [kNear * kNear], column-major in LOGICAL cells
   constexpr int kNearHalf = kNear / 2;
   const uint32_t n_rays = counters[CNT_RAYS];
@@ -320,7 +323,7 @@ raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* _
   const int c_s = static_cast<int>(floorf(gc0));
   const int win_r0 = r_s - kNearHalf, win_c0 = c_s - kNearHalf;
   const int max_steps = nrows + ncols;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   uint32_t* __restrict__ far_x = p.ray_min_enc;
   // float32 start cell inside the map (the precondition tests the origin in float64; the two
   // can disagree by a rounding at the map's edge — those scans take the generic loop below)
@@ -330,16 +333,38 @@ raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* _
   for (int h = threadIdx.x; h < kNear * kNear; h += kBlock) near_x[h] = 0u;
   __syncthreads();
 
-  const uint32_t n_tasks = (n_rays + 31u) >> 5;
-  for (uint32_t task = warp * gridDim.x + blockIdx.x; task < n_tasks; task += (kBlock / 32) * gridDim.x) {
-    const uint32_t i = task * 32u + lane;
-    bool alive = i < n_rays;
-    const float4 pt = alive ? __ldg(&rays[i]) : make_float4(sx, sy, sz, 0.0f);
+  // SEGMENTS.  A DDA is a serial chain (~850 steps for the longest rays here), and a kernel of
+  // one thread per whole ray lasts as long as its longest chain while most SMs idle.  So a ray is
+  // cut into segments of kSeg steps, each its own task: the task for segment k first replays the
+  // k * kSeg earlier steps with the bare recurrence (compare + add: no memory, no bookkeeping —
+  // t_exit and the position are monotone along a ray, so "still running" needs to be checked only
+  // at the end of the replay), then walks its kSeg cells in full.  Same arithmetic, same cells,
+  // ~1.5x the instructions, but the longest chain drops several-fold.
+  const uint32_t n_bundles = (n_rays + 31u) >> 5;
+  const int kSeg = p.seg_len;
+  const uint32_t k_max = static_cast<uint32_t>((max_steps + kSeg - 1) / kSeg);
+  const uint32_t n_tasks = n_bundles * k_max;
+  for (;;) {
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(&counters[CNT_RAY_WORK], 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    // far segments first: they carry the longest replay
+    const int kseg = static_cast<int>(k_max - 1u - task / n_bundles);
+    const uint32_t i = (task % n_bundles) * 32u + lane;
+    const bool have = i < n_rays;
+    const float4 pt = have ? __ldg(&rays[i]) : make_float4(sx, sy, sz, 0.0f);
     const float dz = pt.z - sz;
     const float gr1 = (origin_x - pt.x) / resolution;
     const float gc1 = (origin_y - pt.y) / resolution;
     const float dr = gr1 - gr0;
     const float dc = gc1 - gc0;
+    // cells a ray that stays in the map visits: |rows crossed| + |columns crossed| + 1 (a couple
+    // more or fewer at float edges: the margin below only decides whether the task is looked at)
+    const int n_est = have ? static_cast<int>(fabsf(floorf(gr1) - static_cast<float>(r_s)) +
+                                              fabsf(floorf(gc1) - static_cast<float>(c_s))) + 4 : 0;
+    const int s0 = kseg * kSeg;
+    if (!__any_sync(0xffffffffu, n_est > s0)) continue;   // the whole bundle ends before this segment
     int r = r_s, c = c_s;
     int step_r, step_c;
     float t_r, t_c, td_r, td_c;  // t_max_r / t_max_c / t_delta_r / t_delta_c
@@ -365,17 +390,19 @@ raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* _
     }
 
     if (!start_inside) {
-      // generic traversal, one cell per round trip, every test of the reference's loop.  The map
-      // is convex: once a ray has left it, it never comes back (the reference keeps stepping
-      // through cells that fail its bounds test; stopping there changes nothing).
-      bool was_inside = false;
+      // generic traversal (rare: float32 start cell outside the map), whole ray in one task, one
+      // cell per round trip, every test of the reference's loop.  The map is convex: once a ray
+      // has left it, it never comes back (the reference keeps stepping through cells that fail
+      // its bounds test; stopping there changes nothing).
+      if (kseg != 0) continue;
+      bool alive = have, was_inside = false;
       for (int s = 0; alive && s < max_steps; ++s) {
         const bool row = t_r < t_c;
         const float t_exit = row ? t_r : t_c;   // == min(t_max_r, t_max_c)
         if (static_cast<unsigned>(r) < static_cast<unsigned>(nrows) &&
             static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
           was_inside = true;
-          atomicMax(&far_x[c * nrows + r], __float_as_uint(fminf(t_exit, 1.0f) * dz));
+          atomicMax(&far_x[c * nrows + r], enc_offset(fminf(t_exit, 1.0f) * dz));
         } else if (was_inside) {
           break;
         }
@@ -384,31 +411,66 @@ raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* _
       }
       continue;
     }
-    // Start cell inside the map: every cell reached before the ray steps onto row r_out or
-    // column c_out is inside, so the bounds test is two compares after each step and the
-    // reference's step cap (nrows + ncols) can never bind first.
+
+    // ── replay of the s0 earlier steps: the bare recurrence ──
+    float t_prev = 0.0f;   // t_exit of the last replayed step
+    int nr = 0;            // row steps among them
+    for (int s = 0; s < s0; ++s) {
+      const bool row = t_r < t_c;
+      t_prev = row ? t_r : t_c;
+      if (row) { t_r += td_r; ++nr; } else { t_c += td_c; }
+    }
+    r = r_s + step_r * nr;
+    c = c_s + step_c * (s0 - nr);
+    // Start cell inside the map and monotone movement: every cell reached before the ray steps
+    // onto row r_out or column c_out is inside, so the bounds test is two compares per step and
+    // the reference's step cap (nrows + ncols) can never bind first.
     const int r_out = step_r > 0 ? nrows : -1;      // step_r == 0: r never changes, never equal
     const int c_out = step_c > 0 ? ncols : -1;
     const int dlin_c = step_c * nrows;
+    bool alive = have && t_prev < 1.0f && static_cast<unsigned>(r) < static_cast<unsigned>(nrows) &&
+                 static_cast<unsigned>(c) < static_cast<unsigned>(ncols);
     int lin = c * nrows + r;
+    int left = kSeg;       // steps of this segment still to walk
 
-    // ── near field: shared-memory window around the sensor ──
-    while (alive) {
-      const int wr = r - win_r0, wc = c - win_c0;
-      if (static_cast<unsigned>(wr) >= static_cast<unsigned>(kNear) ||
-          static_cast<unsigned>(wc) >= static_cast<unsigned>(kNear))
-        break;  // left the window: continue in the far field
-      const bool row = t_r < t_c;
-      const float t_exit = row ? t_r : t_c;
-      const uint32_t e = __float_as_uint(fminf(t_exit, 1.0f) * dz);
-      uint32_t* slot = &near_x[wc * kNear + wr];
-      if (e > *slot) atomicMax(slot, e);
-      if (t_exit >= 1.0f) { alive = false; break; }
-      if (row) { r += step_r; t_r += td_r; lin += step_r; } else { c += step_c; t_c += td_c; lin += dlin_c; }
-      alive = r != r_out && c != c_out;
+    // ── near field: shared-memory window around the sensor (first segment only).  The lanes of a
+    // bundle sit on the same window cell most of the time: when they do, the warp writes its best
+    // value with ONE shared atomic instead of 32 conflicting ones ──
+    if (kseg == 0) {
+      for (;;) {
+        const int wr = r - win_r0, wc = c - win_c0;
+        const bool inwin = alive && left > 0 && static_cast<unsigned>(wr) < static_cast<unsigned>(kNear) &&
+                           static_cast<unsigned>(wc) < static_cast<unsigned>(kNear);
+        if (!__any_sync(0xffffffffu, inwin)) break;   // every lane has left the window (or ended)
+        const bool row = t_r < t_c;
+        const float t_exit = row ? t_r : t_c;
+        const uint32_t e = enc_offset(fminf(t_exit, 1.0f) * dz);
+        const int w = inwin ? wc * kNear + wr : 0;
+        const bool want = inwin && e > near_x[w];
+        const uint32_t wm = __ballot_sync(0xffffffffu, want);
+        if (wm) {
+          const int w0 = __shfl_sync(0xffffffffu, w, __ffs(wm) - 1);
+          if (__all_sync(0xffffffffu, !want || w == w0)) {
+            const uint32_t best = __reduce_max_sync(0xffffffffu, want ? e : 0u);
+            if (lane == __ffs(wm) - 1) atomicMax(&near_x[w0], best);
+          } else if (want) {
+            atomicMax(&near_x[w], e);
+          }
+        }
+        if (inwin) {
+          --left;
+          if (t_exit >= 1.0f) {
+            alive = false;
+          } else {
+            if (row) { r += step_r; t_r += td_r; lin += step_r; } else { c += step_c; t_c += td_c; lin += dlin_c; }
+            alive = r != r_out && c != c_out;
+          }
+        }
+      }
     }
 
     // ── far field: global scratch, kRayBatch cells per memory round trip ──
+    alive = alive && left > 0;
     while (__any_sync(0xffffffffu, alive)) {
       int idx[kRayBatch];
       uint32_t ev[kRayBatch];
@@ -417,28 +479,41 @@ raycast_dda_kernel(const __grid_constant__ RaycastParams p, const DeviceState* _
       for (int k = 0; k < kRayBatch; ++k) {
         const bool row = t_r < t_c;
         const float t_exit = row ? t_r : t_c;
-        ev[k] = __float_as_uint(fminf(t_exit, 1.0f) * dz);
+        ev[k] = enc_offset(fminf(t_exit, 1.0f) * dz);
         idx[k] = alive ? lin : -1;
         r += row ? step_r : 0;
         c += row ? 0 : step_c;
         lin += row ? step_r : dlin_c;
         t_r = row ? t_r + td_r : t_r;
         t_c = row ? t_c : t_c + td_c;
-        // the ray ended in that cell (t >= 1), or has just stepped out of the map
-        alive = alive && t_exit < 1.0f && r != r_out && c != c_out;
+        --left;
+        // the ray ended in that cell (t >= 1), has just stepped out of the map, or the segment is done
+        alive = alive && t_exit < 1.0f && r != r_out && c != c_out && left > 0;
       }
+      if (p.tune_ld_cg) {
 #pragma unroll
-      for (int k = 0; k < kRayBatch; ++k) cv[k] = idx[k] >= 0 ? far_x[idx[k]] : 0xffffffffu;
+        for (int k = 0; k < kRayBatch; ++k) cv[k] = idx[k] >= 0 ? __ldcg(&far_x[idx[k]]) : 0xffffffffu;
+      } else {
+#pragma unroll
+        for (int k = 0; k < kRayBatch; ++k) cv[k] = idx[k] >= 0 ? far_x[idx[k]] : 0xffffffffu;
+      }
 #pragma unroll
       for (int k = 0; k < kRayBatch; ++k) {
         const bool want = ev[k] > cv[k];
-        if (__any_sync(0xffffffffu, want)) {  // warp-uniform: every lane takes part in the election
-          // lanes that lower the same cell elect the one with the lowest ray (lowest lane on a
-          // tie); lanes with nothing to write get a key of their own
-          const uint32_t peers = __match_any_sync(0xffffffffu, want ? idx[k] : -(lane + 2));
-          const uint32_t best = __reduce_max_sync(peers, want ? ev[k] : 0u);
-          const uint32_t winners = __ballot_sync(0xffffffffu, want && ev[k] == best);
-          if (want && ev[k] == best && (__ffs(winners & peers) - 1) == lane) atomicMax(&far_x[idx[k]], best);
+        if (p.tune_elect == 0) {
+          if (want) atomicMax(&far_x[idx[k]], ev[k]);
+        } else {
+          // bundle fast path: when every writing lane is on the same cell, one lane writes the warp's best
+          const uint32_t wm = __ballot_sync(0xffffffffu, want);
+          if (wm) {
+            const int i0 = __shfl_sync(0xffffffffu, idx[k], __ffs(wm) - 1);
+            if (__all_sync(0xffffffffu, !want || idx[k] == i0)) {
+              const uint32_t best = __reduce_max_sync(0xffffffffu, want ? ev[k] : 0u);
+              if (lane == __ffs(wm) - 1) atomicMax(&far_x[i0], best);
+            } else if (want) {
+              atomicMax(&far_x[idx[k]], ev[k]);
+            }
+          }
         }
       }
     }
@@ -546,6 +621,50 @@ inpaint_iter_kernel(const float* __restrict__ src, float* __restrict__ dst,
           const int nbr = wrap_index(nr + g.start[0], g.rows);
           const int nbc = wrap_index(nc + g.start[1], g.cols);
           const float val = src[static_cast<size_t>(nbc) * rows_local + nbr];
+          if (isfinite(val)) {
+            sum += val;
+            ++count;
+          }
+        }
+      }
+      if (count >= min_valid) out = sum / static_cast<float>(count);
+    }
+    dst[i] = out;
+  }
+}
+
+// The same sweep on one ROW STRIPE of a GLOBAL map (start index 0): the logical rows just above
+// and below the stripe belong to the neighbouring ranks and arrive as two rows of `cols` floats
+// (null at the map's border) — the halo the sharded driver exchanges between sweeps.
+__global__ void __launch_bounds__(kBlock)
+inpaint_stripe_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows_local, int cols,
+                      const float* __restrict__ above, const float* __restrict__ below, int min_valid) {
+  const size_t n = static_cast<size_t>(rows_local) * cols;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = src[i];
+    float out = v;
+    if (isnan(v)) {
+      const int c = static_cast<int>(i / rows_local);
+      const int r = static_cast<int>(i - static_cast<size_t>(c) * rows_local);
+      float sum = 0.0f;
+      int count = 0;
+      for (int dr = -1; dr <= 1; ++dr) {
+        for (int dc = -1; dc <= 1; ++dc) {
+          if (dr == 0 && dc == 0) continue;
+          const int nr = r + dr, nc = c + dc;
+          if (nc < 0 || nc >= cols) continue;
+          float val;
+          if (nr < 0) {
+            if (!above) continue;
+            val = above[nc];
+          } else if (nr >= rows_local) {
+            if (!below) continue;
+            val = below[nc];
+          } else {
+            val = src[static_cast<size_t>(nc) * rows_local + nr];
+          }
           if (isfinite(val)) {
             sum += val;
             ++count;
@@ -1073,11 +1192,13 @@ void launch_voxel_select32(const uint32_t* sorted_keys, const uint32_t* sorted_v
       sorted_keys, sorted_vals, n, invalid_key, counters, out_sel);
   ++lc.mine;
 }
-size_t ray_sort_scratch_words() { return 2 * static_cast<size_t>(kRayBins); }
+// histogram [kRayBins] | cursors [kRayBins] | rays per length bin [kRayLenBins]
+size_t ray_sort_scratch_words() { return 2 * static_cast<size_t>(kRayBins) + kRayLenBins; }
+static_assert(kRayLenBins == 32, "ray_bin_scan_kernel sums the length-bin totals with one warp");
 
 static void launch_ray_bundle_sort(const RaySortScratch& rs, uint32_t n_max, const uint32_t* counters,
                                    cudaStream_t s, LaunchCounter& lc) {
-  ray_bin_scan_kernel<<<1, 1024, 0, s>>>(rs.hist, rs.hist + kRayBins);
+  ray_bin_scan_kernel<<<kRayLenBins, kRayAzBins, 0, s>>>(rs.hist, rs.hist + kRayBins);
   const uint32_t want = (n_max + kBlock - 1) / kBlock;
   ray_bin_scatter_kernel<<<want < 148u * 4u ? want : 148u * 4u, kBlock, 0, s>>>(rs.unsorted, rs.rays,
                                                                               rs.hist + kRayBins, counters);
@@ -1104,7 +1225,7 @@ void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sor
   launch_ray_bundle_sort(rs, n, counters, s, lc);
 }
 void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
-                        uint32_t n_max, const uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+                        uint32_t n_max, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
   if (n_max == 0) return;
   // near-field window size / persistent CTAs per SM (FDEM_RAY_NEAR=64|96|128 overrides)
   static int near = -1;
@@ -1118,13 +1239,17 @@ void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const flo
     const size_t smem = sizeof(uint32_t) * kn * kn;
     // opt-in to > 48 KiB of dynamic shared memory (per device, so not cached in a static)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    const uint32_t want = (chunks + (kBlock / 32) - 1) / (kBlock / 32);
+    static const int ctas_env = [] { const char* e = std::getenv("FDEM_RAY_CTAS"); return e ? std::atoi(e) : 0; }();
+    if (ctas_env > 0 && static_cast<uint32_t>(ctas_env) < ctas_per_sm) ctas_per_sm = static_cast<uint32_t>(ctas_env);
+    const uint32_t want = (chunks + (kBlock / 32) - 1) / (kBlock / 32) * 4u;   // ~4 segment tasks per bundle
     const uint32_t grid = want < 148u * ctas_per_sm ? want : 148u * ctas_per_sm;
     kernel<<<grid, kBlock, smem, s>>>(p, st, rays, counters);
   };
-  if (near == 64) launch(raycast_dda_kernel<64>, 64, 8u);
-  else if (near == 96) launch(raycast_dda_kernel<96>, 96, 5u);
-  else launch(raycast_dda_kernel<128>, 128, 3u);
+  static const int occ = [] { const char* e = std::getenv("FDEM_RAY_OCC"); return e ? std::atoi(e) : 0; }();
+  if (near == 64 && occ == 8) launch(raycast_dda_kernel<64, 8>, 64, 8u);
+  else if (near == 64) launch(raycast_dda_kernel<64, 6>, 64, 6u);
+  else if (near == 96) launch(raycast_dda_kernel<96, 4>, 96, 5u);
+  else launch(raycast_dda_kernel<128, 3>, 128, 3u);
   ++lc.mine;
 }
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st,
@@ -1207,6 +1332,12 @@ void launch_pack_pointcloud2(const float* elev, const float* const* fields, int 
     pack_write_kernel<<<grid, kBlock, 0, s>>>(p, st, col_offset, out);
     ++lc.mine;
   }
+}
+void launch_inpaint_stripe(const float* src, float* dst, int rows_local, int cols, const float* above,
+                           const float* below, int min_valid, cudaStream_t s, LaunchCounter& lc) {
+  inpaint_stripe_kernel<<<grid_for(static_cast<size_t>(rows_local) * cols, kBlock), kBlock, 0, s>>>(
+      src, dst, rows_local, cols, above, below, min_valid);
+  ++lc.mine;
 }
 void launch_inpaint_iter(const float* src, float* dst, const DeviceState* st, int min_valid,
                          cudaStream_t s, LaunchCounter& lc, int rows_local, int cols) {

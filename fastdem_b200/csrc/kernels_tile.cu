@@ -652,6 +652,9 @@ shard_gather_kernel(const __grid_constant__ ShardBackArgs a, uint32_t* __restric
   const uint32_t prev = a.st_cur->touched_count;
   const uint32_t flags_in = a.st_cur->flags;
   if (tid == 0) {
+    // the scan's statistics as this rank saw them: kept / inside points of its slice
+    counters[CNT_KEPT] = a.front_counters[CNT_KEPT];
+    counters[CNT_INSIDE] = a.front_counters[CNT_INSIDE];
     a.st_out->geom = a.st_cur->geom;  // GLOBAL maps never move
     a.st_out->touched_count = scan_inside > 0 ? 0u : prev;
     uint32_t flags = flags_in;

@@ -41,6 +41,20 @@ using Vector3d = VectorN<double, 3>;
 using Vector3f = VectorN<float, 3>;
 using Vector2i = VectorN<int, 2>;
 
+// column-major 3x3 float — what SensorModel::computeCovariance returns and the cloud's
+// covariance channel stores (36 bytes, nanopcl/core/types.hpp:46-52)
+struct Matrix3f {
+  float m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static Matrix3f Zero() { return Matrix3f(); }
+  static Matrix3f Identity() { Matrix3f r; r.m[0] = r.m[4] = r.m[8] = 1.0f; return r; }
+  float& operator()(int r, int c) { return m[c * 3 + r]; }
+  float operator()(int r, int c) const { return m[c * 3 + r]; }
+  const float* data() const { return m; }
+  float* data() { return m; }
+  Matrix3f operator*(float s) const { Matrix3f r; for (int i = 0; i < 9; ++i) r.m[i] = m[i] * s; return r; }
+};
+inline Matrix3f operator*(float s, const Matrix3f& a) { return a * s; }
+
 // column-major 4x4, bottom row (0,0,0,1)
 class Isometry3d {
  public:

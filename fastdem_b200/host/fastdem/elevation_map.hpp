@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cmath>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -55,9 +56,11 @@ class ElevationMap {
   ElevationMap(const ElevationMap&) = delete;
   ElevationMap& operator=(const ElevationMap&) = delete;
 
+  // nanoGrid setGeometry + clearAll (elevation_map.hpp:112-116).  On an existing map the resize
+  // happens IN PLACE: the handle — and every FastDEM holding this map by reference — stays valid.
   void setGeometry(float width, float height, float resolution) {
-    if (h_) { fdem_map_destroy(h_); h_ = nullptr; }
-    check(fdem_map_create(width, height, resolution, device_, nullptr, &h_));
+    if (h_) check(fdem_map_set_geometry(h_, width, height, resolution));
+    else check(fdem_map_create(width, height, resolution, device_, nullptr, &h_));
   }
   bool isInitialized() const { return h_ != nullptr; }
   fdem_map* handle() const { return h_; }
@@ -123,6 +126,25 @@ class ElevationMap {
     check(fdem_map_cell_get(h_, name.c_str(), idx(0), idx(1), &v));
     return v;
   }
+  // GridMap::at returns float&: `map.at(layer, idx) = v;` and `float v = map.at(layer, idx);` both
+  // work through this proxy (the cell lives in HBM; a read or a write is one small transfer)
+  class CellRef {
+   public:
+    operator float() const { return map_->at(static_cast<const std::string&>(name_), idx_); }
+    CellRef& operator=(float v) { map_->setAt(name_, idx_, v); return *this; }
+    CellRef& operator=(const CellRef& o) { return *this = static_cast<float>(o); }
+    CellRef& operator+=(float v) { return *this = static_cast<float>(*this) + v; }
+    CellRef& operator-=(float v) { return *this = static_cast<float>(*this) - v; }
+
+   private:
+    friend class ElevationMap;
+    CellRef(ElevationMap* m, std::string n, nanogrid::Index i) : map_(m), name_(std::move(n)), idx_(i) {}
+    const ElevationMap* cmap() const { return map_; }
+    ElevationMap* map_;
+    std::string name_;
+    nanogrid::Index idx_;
+  };
+  CellRef at(const std::string& name, const nanogrid::Index& idx) { return CellRef(this, name, idx); }
   void setAt(const std::string& name, const nanogrid::Index& idx, float v) {
     check(fdem_map_cell_set(h_, name.c_str(), idx(0), idx(1), v));
   }
@@ -141,6 +163,29 @@ class ElevationMap {
   float elevationAt(const nanogrid::Index& idx) const { return at(layer::elevation, idx); }
   bool hasElevationAt(const nanogrid::Position& p) const { return std::isfinite(elevationAt(p)); }
   bool hasElevationAt(const nanogrid::Index& idx) const { return std::isfinite(elevationAt(idx)); }
+  // ElevationMap::snapshot (elevation_map.hpp:161-177): a second map with the same geometry,
+  // position, start index and frame holding copies of the named layers (missing names skipped).
+  // Device-to-host-to-device here: the post-process timer of the ROS node calls it at 1-2 Hz.
+  void snapshot(ElevationMap& snap, std::initializer_list<std::string> layers) const {
+    auto g = geom();
+    snap.device_ = device_;
+    snap.setGeometry(static_cast<float>(g.length[0]), static_cast<float>(g.length[1]), static_cast<float>(g.resolution));
+    snap.setFrameId(getFrameId());
+    snap.setPosition(getPosition());
+    snap.setStartIndex(getStartIndex());
+    for (const auto& name : layers) {
+      if (!exists(name)) continue;
+      if (!snap.exists(name)) snap.add(name);
+      snap.set(name, get(name));
+    }
+  }
+  // move construction only (the handle is unique), so `auto snap = map.snapshot({...})` works
+  ElevationMap(ElevationMap&& o) noexcept : h_(o.h_), device_(o.device_), frame_id_(std::move(o.frame_id_)) { o.h_ = nullptr; }
+  ElevationMap snapshot(std::initializer_list<std::string> layers) const {
+    ElevationMap snap;
+    snapshot(snap, layers);
+    return snap;
+  }
 
  private:
   fdem_geometry geom() const {

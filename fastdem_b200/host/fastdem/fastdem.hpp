@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <functional>
+#include <limits>
 #include <memory>
 #include <optional>
 #include <string>
@@ -13,6 +14,7 @@
 #include "fastdem/config.hpp"
 #include "fastdem/elevation_map.hpp"
 #include "fastdem/point_types.hpp"
+#include "fastdem/sensors.hpp"
 
 namespace fastdem {
 
@@ -47,7 +49,18 @@ class FastDEM {
 
   FastDEM& setMappingMode(MappingMode mode) { cfg_.mapping.mode = mode; return push(); }
   FastDEM& setEstimatorType(EstimationType t) { cfg_.mapping.estimation_type = t; return push(); }
-  FastDEM& setSensorModel(SensorType t) { cfg_.sensor_model.type = t; return push(); }
+  FastDEM& setSensorModel(SensorType t) {
+    cfg_.sensor_model.type = t;
+    custom_model_.reset();  // fastdem.cpp:40-44: the setter re-creates the model from the config
+    return push();
+  }
+  // The reference's extension point (fastdem.hpp:80): any SensorModel subclass.  It cannot run on
+  // the device, so integrate() evaluates model->computeCovariances() on the host and passes the
+  // per-point sensor-frame covariances through fdem_mapper_integrate_with_cov.
+  FastDEM& setSensorModel(std::unique_ptr<SensorModel> model) {
+    if (model) custom_model_ = std::move(model);
+    return *this;
+  }
   FastDEM& setHeightFilter(float z_min, float z_max) noexcept {
     cfg_.point_filter.z_min = z_min; cfg_.point_filter.z_max = z_max; return push();
   }
@@ -108,19 +121,59 @@ class FastDEM {
     check(fdem_mapper_set_config(h_, &a));
     return *this;
   }
+  // R * S * R^T in float, tmp = R*S first, 3-term dots as a0 + (a1 + a2): the evaluation order the
+  // oracle fixes for fastdem.cpp:184-187
+  static Eigen::Matrix3f rotateCov(const float R[9], const Eigen::Matrix3f& S) {
+    auto Rm = [&](int r, int c) { return R[c * 3 + r]; };
+    float T[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) T[i][j] = Rm(i, 0) * S(0, j) + (Rm(i, 1) * S(1, j) + Rm(i, 2) * S(2, j));
+    Eigen::Matrix3f out = Eigen::Matrix3f::Zero();
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) out(i, j) = T[i][0] * Rm(j, 0) + (T[i][1] * Rm(j, 1) + T[i][2] * Rm(j, 2));
+    return out;
+  }
+
   bool integrateImpl(const PointCloud& cloud, const Eigen::Isometry3d& Tbs, const Eigen::Isometry3d& Twb) {
-    check(fdem_mapper_integrate(h_, cloud.xyzw(), cloud.intensities(), cloud.colors(), cloud.size(),
-                                Tbs.matrix().data(), Twb.matrix().data(), &stats_));
+    if (custom_model_) {
+      // preprocessScan's first step on the host (fastdem.cpp:171), the rest on the device
+      const PointCloud with_cov = custom_model_->computeCovariances(cloud);
+      static_assert(sizeof(Eigen::Matrix3f) == 9 * sizeof(float), "covariances are passed as N x 9 floats");
+      check(fdem_mapper_integrate_with_cov(h_, cloud.xyzw(), with_cov.covariances().data()->data(),
+                                           cloud.intensities(), cloud.colors(), cloud.size(),
+                                           Tbs.matrix().data(), Twb.matrix().data(), &stats_));
+    } else {
+      check(fdem_mapper_integrate(h_, cloud.xyzw(), cloud.intensities(), cloud.colors(), cloud.size(),
+                                  Tbs.matrix().data(), Twb.matrix().data(), &stats_));
+    }
     if (!stats_.integrated) return false;  // all points filtered (fastdem.cpp:138)
     if (on_preprocessed_) {
+      // the preprocessed cloud in the map frame WITH its covariance channel (fastdem.cpp:139-141,
+      // 181-187).  The device keeps only sigma_z^2 = cov(2,2), so the full 3x3 is rebuilt here from
+      // the source points: sensor-frame model covariance, rotated by R = (T_wb * T_bs).rotation().
       int64_t n = 0;
       check(fdem_mapper_last_preprocessed(h_, nullptr, nullptr, nullptr, &n));
       std::vector<float> xyzw(static_cast<size_t>(n > 0 ? n : 1) * 4);
-      check(fdem_mapper_last_preprocessed(h_, xyzw.data(), nullptr, nullptr, &n));
+      std::vector<int32_t> src(static_cast<size_t>(n > 0 ? n : 1));
+      check(fdem_mapper_last_preprocessed(h_, xyzw.data(), nullptr, src.data(), &n));
       xyzw.resize(static_cast<size_t>(n) * 4);
       for (int64_t i = 0; i < n; ++i) xyzw[4 * i + 3] = 1.0f;  // slot 3 carried sigma_z^2
       PointCloud pc;
       pc.setPointsXYZW(std::move(xyzw));
+      pc.useCovariance();
+      double M[16];
+      const double* a = Twb.matrix().data();
+      const double* b = Tbs.matrix().data();
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          M[j * 4 + i] = (a[0 * 4 + i] * b[j * 4 + 0] + a[1 * 4 + i] * b[j * 4 + 1]) + a[2 * 4 + i] * b[j * 4 + 2];
+      float R[9];
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) R[c * 3 + r] = static_cast<float>(M[c * 4 + r]);
+      const std::unique_ptr<SensorModel> builtin = custom_model_ ? nullptr : createSensorModel(cfg_.sensor_model);
+      const SensorModel& model = custom_model_ ? *custom_model_ : *builtin;
+      for (int64_t i = 0; i < n; ++i)
+        pc.covariance(static_cast<size_t>(i)) = rotateCov(R, model.computeCovariance(cloud.point(static_cast<size_t>(src[i]))));
       pc.setFrameId(map_.getFrameId());
       on_preprocessed_(pc);
     }
@@ -143,8 +196,77 @@ class FastDEM {
   fdem_scan_stats stats_{};
   std::shared_ptr<Calibration> calibration_;
   std::shared_ptr<Odometry> odometry_;
+  std::unique_ptr<SensorModel> custom_model_;  // null: the built-in model of cfg_.sensor_model runs on the device
   CloudCallback on_preprocessed_, on_rasterized_;
 };
+
+// fastdem::ElevationMapping (fastdem/include/fastdem/mapping/elevation_mapping.hpp:20-64): the
+// lower seam the reference's test_dual_layer.cpp drives directly — points already in the map
+// frame, cloud.covariance(i)(2,2) as the measurement variance, robot position for LOCAL maps.
+class ElevationMapping {
+ public:
+  struct CellObservation {  // elevation_mapping.hpp:26-34; the device reports min_z per touched cell
+    float min_z = std::numeric_limits<float>::max();
+    float min_z_var = 0.0f;
+    float max_z = std::numeric_limits<float>::lowest();
+    float max_intensity = std::numeric_limits<float>::lowest();
+    float color_packed = 0.0f;
+    bool has_intensity = false;
+    bool has_color = false;
+  };
+  // CellMap<CellObservation> of the reference is an unordered_map keyed by Index; iteration order
+  // is unspecified there, a vector of (cell centre, observation) here
+  struct Entry {
+    nanogrid::Position position;
+    CellObservation obs;
+  };
+  using CellObservations = std::vector<Entry>;
+
+  ElevationMapping(ElevationMap& map, const config::Mapping& cfg) : map_(map) {
+    Config c;
+    c.mapping = cfg;
+    fdem_config a = toAbi(c);
+    check(fdem_mapper_create(map_.handle(), &a, &h_));  // ensureLayers + obstacle (elevation_mapping.cpp:11-39)
+  }
+  ~ElevationMapping() { if (h_) fdem_mapper_destroy(h_); }
+  ElevationMapping(const ElevationMapping&) = delete;
+  ElevationMapping& operator=(const ElevationMapping&) = delete;
+
+  // rasterize + estimate (+ min/max, obstacle, intensity, colour) in one call (elevation_mapping.cpp:110-125)
+  CellObservations update(const PointCloud& cloud, const Eigen::Vector2d& robot_position) {
+    std::vector<float> var_z;
+    if (cloud.hasCovariance()) {
+      var_z.resize(cloud.size());
+      for (size_t i = 0; i < cloud.size(); ++i) var_z[i] = cloud.covariance(i)(2, 2);  // :58-60
+    }
+    fdem_scan_stats st{};
+    check(fdem_mapper_update(h_, cloud.xyzw(), var_z.empty() ? nullptr : var_z.data(), cloud.intensities(),
+                             cloud.colors(), cloud.size(), robot_position(0), robot_position(1), &st));
+    CellObservations out;
+    if (st.n_cells > 0) {
+      int64_t n = 0;
+      check(fdem_mapper_last_rasterized(h_, nullptr, &n));
+      std::vector<float> xyz(static_cast<size_t>(n > 0 ? n : 1) * 3);
+      check(fdem_mapper_last_rasterized(h_, xyz.data(), &n));
+      out.resize(static_cast<size_t>(n));
+      for (int64_t i = 0; i < n; ++i) {
+        out[i].position = nanogrid::Position(xyz[3 * i], xyz[3 * i + 1]);
+        out[i].obs.min_z = xyz[3 * i + 2];
+        out[i].obs.has_intensity = cloud.hasIntensity();
+        out[i].obs.has_color = cloud.hasColor();
+      }
+    }
+    return out;
+  }
+
+ private:
+  ElevationMap& map_;
+  fdem_mapper* h_ = nullptr;
+};
+
+inline std::unique_ptr<ElevationMapping> createElevationMapping(ElevationMap& map, const config::Mapping& cfg) {
+  return std::make_unique<ElevationMapping>(map, cfg);
+}
 
 // fastdem::applyRaycasting (fastdem/include/fastdem/postprocess/raycasting.hpp:49-51)
 inline void applyRaycasting(ElevationMap& map, const PointCloud& scan, const Eigen::Vector3f& sensor_origin,

@@ -26,12 +26,13 @@ class PointCloud {
   size_t size() const { return xyzw_.size() / 4; }
   bool empty() const { return xyzw_.empty(); }
   void reserve(size_t n) { xyzw_.reserve(n * 4); }
-  void clear() { xyzw_.clear(); intensity_.clear(); color_.clear(); }
+  void clear() { xyzw_.clear(); intensity_.clear(); color_.clear(); cov_.clear(); }
 
   void add(float x, float y, float z) {  // impl/point_cloud_impl.hpp:116-119 — w = 1
     xyzw_.push_back(x); xyzw_.push_back(y); xyzw_.push_back(z); xyzw_.push_back(1.0f);
     if (use_intensity_) intensity_.push_back(0.0f);
     if (use_color_) { color_.push_back(0); color_.push_back(0); color_.push_back(0); }
+    if (use_cov_) cov_.emplace_back();
   }
   void add(float x, float y, float z, Intensity i) {
     if (!use_intensity_) useIntensity();
@@ -47,6 +48,13 @@ class PointCloud {
   bool hasColor() const { return use_color_; }
   void useIntensity() { use_intensity_ = true; intensity_.resize(size(), 0.0f); }
   void useColor() { use_color_ = true; color_.resize(size() * 3, 0); }
+  // covariance channel (point_cloud.hpp: useCovariance / covariances / covariance(i))
+  bool hasCovariance() const { return use_cov_; }
+  void useCovariance() { use_cov_ = true; cov_.resize(size()); }
+  std::vector<Eigen::Matrix3f>& covariances() { return cov_; }
+  const std::vector<Eigen::Matrix3f>& covariances() const { return cov_; }
+  Eigen::Matrix3f& covariance(size_t i) { return cov_[i]; }
+  const Eigen::Matrix3f& covariance(size_t i) const { return cov_[i]; }
 
   const float* xyzw() const { return xyzw_.data(); }
   const float* intensities() const { return use_intensity_ ? intensity_.data() : nullptr; }
@@ -54,7 +62,10 @@ class PointCloud {
   Eigen::Vector3f point(size_t i) const {
     return Eigen::Vector3f(xyzw_[4 * i], xyzw_[4 * i + 1], xyzw_[4 * i + 2]);
   }
-  void setPointsXYZW(std::vector<float> xyzw) { xyzw_ = std::move(xyzw); }
+  void setPointsXYZW(std::vector<float> xyzw) {
+    xyzw_ = std::move(xyzw);
+    if (use_cov_) cov_.resize(size());
+  }
 
   const std::string& frameId() const { return frame_id_; }
   void setFrameId(const std::string& id) { frame_id_ = id; }
@@ -65,9 +76,10 @@ class PointCloud {
   std::vector<float> xyzw_;
   std::vector<float> intensity_;
   std::vector<uint8_t> color_;
+  std::vector<Eigen::Matrix3f> cov_;
   std::string frame_id_;
   uint64_t timestamp_ns_ = 0;
-  bool use_intensity_ = false, use_color_ = false;
+  bool use_intensity_ = false, use_color_ = false, use_cov_ = false;
 };
 
 }  // namespace nanopcl

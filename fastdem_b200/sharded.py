@@ -36,11 +36,48 @@ class CudaStripe:
     """Product engine: this rank's stripe as a device-resident map + mapper."""
 
     def __init__(self, width, height, resolution, cfg, r0, r1, device=0, stream=0):
-        from . import api
+        from . import api, capi
         self.map = api.ElevationMap(width, height, resolution, "map", device=device, stream=stream,
                                     row_stripe=(r0, r1))
         self.dem = api.FastDEM(self.map, cfg)
-        self._api = api
+        self._api, self._capi = api, capi
+        self.device = device
+
+    def torch_stream(self):
+        """Context manager that makes the MAP's stream torch's current stream.  Collectives order
+        their buffers against torch's current stream only (dist.broadcast of a scan, the halo
+        send / recv of the stencils), and so do torch copies: everything that touches data the
+        map's kernels read or write must be issued inside this context."""
+        import torch
+        return torch.cuda.stream(torch.cuda.ExternalStream(self.map.stream(), device=self.device))
+
+    # ── stencil post-processing on the stripe: device resident, halo rows as device tensors ──
+    def inpaint_begin(self):
+        """`elevation_inpainted` = copy of `elevation` (applyInpainting, inplace = false)."""
+        if not self.map.exists("elevation_inpainted"):
+            self.map.add("elevation_inpainted")
+        self.map.tensor("elevation_inpainted").copy_(self.map.tensor("elevation"))
+
+    def border_rows(self, name):
+        """(first row, last row) of the stripe as contiguous device tensors of `cols` floats."""
+        t = self.map.tensor(name)            # (cols, rows_local) view of the column-major slab
+        return t[:, 0].contiguous(), t[:, -1].contiguous()
+
+    def inpaint_sweep(self, name, above, below, min_valid):
+        """One Jacobi sweep in place; above / below: device tensors (cols floats) or None."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        # (with a CPU process group — the one-GPU tests — the halo rows arrive on the host)
+        above = None if above is None else above.to(dev).contiguous()
+        below = None if below is None else below.to(dev).contiguous()
+        self._halo = (above, below)   # alive until the sweep has run
+        lib = self._capi.load_library()
+        self._capi.check(lib.fdem_inpaint_stripe_sweep(
+            self.map.handle, name.encode(), None if above is None else above.data_ptr(),
+            None if below is None else below.data_ptr(), int(min_valid)))
+
+    def result(self, name):
+        return self.map.get(name)
 
     def integrate(self, xyzw, intensity, rgb, Tbs, Twb):
         cloud = self._api.PointCloud()
@@ -145,18 +182,27 @@ class ShardedGlobalMap:
         return conv(px), conv(pi), conv(pc)
 
     # ── FastDEM::integrate on the sharded map ──
+    def _stream_ctx(self):
+        # the engine's stream as torch's current stream (CUDA engine); nothing to order on CPU
+        import contextlib
+        return self.engine.torch_stream() if hasattr(self.engine, "torch_stream") else contextlib.nullcontext()
+
     def integrate(self, xyzw=None, intensity=None, rgb=None, T_base_sensor=None, T_world_base=None,
                   src: int = 0):
-        px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
-        a, b, c = self._engine_inputs(px, pi, pc)
-        return self.engine.integrate(a, b, c, Tbs, Twb)
+        with self._stream_ctx():   # the broadcast and the kernels that consume it share one stream
+            px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
+            a, b, c = self._engine_inputs(px, pi, pc)
+            return self.engine.integrate(a, b, c, Tbs, Twb)
 
     def integrate_async(self, xyzw=None, intensity=None, rgb=None, T_base_sensor=None,
                         T_world_base=None, src: int = 0):
-        px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
-        a, b, c = self._engine_inputs(px, pi, pc)
-        self._keep = (px, pi, pc)
-        self.engine.integrate_async(a, b, c, Tbs, Twb)
+        # same stream for the broadcasts and the kernels: scan k+1's broadcast into the reused
+        # receive buffers cannot overtake scan k's kernels, and K1 cannot start before its scan landed
+        with self._stream_ctx():
+            px, pi, pc, Tbs, Twb = self.broadcast_scan(xyzw, intensity, rgb, T_base_sensor, T_world_base, src)
+            a, b, c = self._engine_inputs(px, pi, pc)
+            self._keep = (px, pi, pc)
+            self.engine.integrate_async(a, b, c, Tbs, Twb)
 
     def wait(self):
         return self.engine.wait()
@@ -191,18 +237,19 @@ class ShardedGlobalMap:
             self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
         return bool(int(flag.item()))
 
-    def exchange_halo_rows(self, layer_rows_top: np.ndarray, layer_rows_bottom: np.ndarray):
+    def exchange_halo_rows(self, send_top, send_bot):
         """One boundary row to each neighbour stripe (3x3 stencils need exactly one): returns
-        (row above my first row, row below my last row), NaN rows at the map border."""
+        (row above my first row, row below my last row); None at the map border.  The rows are
+        tensors on the communication device (CUDA with NCCL: the exchange is ordered on the
+        map's stream, between two sweeps, and nothing touches the host)."""
         torch, dist = self.torch, self.dist
-        nan_row = np.full(self.cols, np.nan, np.float32)
         if self.world == 1:
-            return nan_row, nan_row.copy()
+            return None, None
         up, down = self.rank - 1, self.rank + 1
-        send_top = torch.from_numpy(np.ascontiguousarray(layer_rows_top, np.float32)).to(self.comm_device)
-        send_bot = torch.from_numpy(np.ascontiguousarray(layer_rows_bottom, np.float32)).to(self.comm_device)
-        recv_above = torch.full((self.cols,), float("nan"), dtype=torch.float32, device=self.comm_device)
-        recv_below = torch.full((self.cols,), float("nan"), dtype=torch.float32, device=self.comm_device)
+        send_top = send_top.to(self.comm_device).contiguous()
+        send_bot = send_bot.to(self.comm_device).contiguous()
+        recv_above = torch.empty_like(send_top) if up >= 0 else None
+        recv_below = torch.empty_like(send_bot) if down < self.world else None
         ops = []
         if up >= 0:
             ops += [dist.P2POp(dist.isend, send_top, up, self.group), dist.P2POp(dist.irecv, recv_above, up, self.group)]
@@ -210,35 +257,21 @@ class ShardedGlobalMap:
             ops += [dist.P2POp(dist.isend, send_bot, down, self.group), dist.P2POp(dist.irecv, recv_below, down, self.group)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        return recv_above.cpu().numpy(), recv_below.cpu().numpy()
+        return recv_above, recv_below
 
     def inpaint(self, max_iterations: int = 3, min_valid_neighbors: int = 2):
-        """applyInpainting (fastdem/src/inpainting.cpp:21-67) on the sharded `elevation` layer →
-        `elevation_inpainted` stripes, one halo-row exchange per sweep.  Host-side stencil on the
-        stripe (post-processing, not the hot path); returns this rank's stripe."""
-        cur = np.asarray(self.engine.get("elevation"), np.float32).copy()
-        R = cur.shape[0]
-        for _ in range(max_iterations):
-            above, below = self.exchange_halo_rows(cur[0], cur[-1])
-            padded = np.full((R + 2, self.cols + 2), np.nan, np.float32)
-            padded[1:-1, 1:-1] = cur
-            padded[0, 1:-1] = above
-            padded[-1, 1:-1] = below
-            total = np.zeros((R, self.cols), np.float32)
-            count = np.zeros((R, self.cols), np.int32)
-            for dr in (-1, 0, 1):          # the oracle's neighbour order: dr outer, dc inner
-                for dc in (-1, 0, 1):
-                    if dr == 0 and dc == 0:
-                        continue
-                    nb = padded[1 + dr: 1 + dr + R, 1 + dc: 1 + dc + self.cols]
-                    ok = np.isfinite(nb)
-                    total = np.where(ok, total + np.where(ok, nb, np.float32(0)), total).astype(np.float32)
-                    count += ok
-            fill = np.isnan(cur) & (count >= min_valid_neighbors)
-            nxt = cur.copy()
-            nxt[fill] = (total[fill] / count[fill].astype(np.float32)).astype(np.float32)
-            cur = nxt
-        return cur
+        """applyInpainting (fastdem/src/inpainting.cpp:21-67) on the sharded `elevation` layer ->
+        `elevation_inpainted` stripes: per sweep, one halo row to / from each neighbour, then the
+        engine's stencil kernel on the stripe (fdem_inpaint_stripe_sweep for the CUDA engine).
+        Returns this rank's stripe of the result."""
+        eng = self.engine
+        with self._stream_ctx():
+            eng.inpaint_begin()
+            for _ in range(max_iterations):
+                top, bot = eng.border_rows("elevation_inpainted")
+                above, below = self.exchange_halo_rows(top, bot)
+                eng.inpaint_sweep("elevation_inpainted", above, below, min_valid_neighbors)
+            return eng.result("elevation_inpainted")
 
 
 class ShardedMapper:

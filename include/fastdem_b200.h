@@ -318,6 +318,13 @@ fdem_status fdem_raycast(fdem_map* map, const float* xyzw, size_t n, const float
  * oracle defines (sort on (key, index)). */
 fdem_status fdem_voxel_grid_any(fdem_map* map, const float* xyzw, size_t n, float voxel_size,
                                 uint32_t* out_index, int64_t* n_voxels);
+/* One Jacobi sweep of applyInpainting (fastdem/src/inpainting.cpp:41-62) on a ROW STRIPE of a
+ * GLOBAL map, in place on `layer` (snapshot in, layer out).  The logical rows just above / below
+ * the stripe live on the neighbouring ranks: they are passed as DEVICE pointers to `cols` floats
+ * each (NULL at the map border) — the 1-row halo the sharded driver exchanges (NCCL send / recv on
+ * the map's stream) between sweeps.  Asynchronous on the map's stream. */
+fdem_status fdem_inpaint_stripe_sweep(fdem_map* map, const char* layer, const float* halo_above,
+                                      const float* halo_below, int32_t min_valid_neighbors);
 /* fastdem::applyInpainting(map, max_iterations, min_valid_neighbors, inplace)
  * (fastdem/src/inpainting.cpp:21-67) */
 fdem_status fdem_inpaint(fdem_map* map, int32_t max_iterations, int32_t min_valid_neighbors,

@@ -104,7 +104,7 @@ def test_set_geometry_in_place_keeps_the_mapper_valid(fdem, tmp_path):
     assert np.isnan(gmap.get("elevation")).all() and np.isnan(gmap.get("n_points")).all()
     omap2 = ob.OracleMap(6.0, 8.0, 0.25)
     odem2 = ob.OracleFastDEM(omap2, cfg)
-    omap2.clear_all()                             # setGeometry + clearAll: estimator layers are NaN too
+    omap2.clearAll()                              # setGeometry + clearAll: estimator layers are NaN too
     _both(fdem, gdem, odem2, pts)                  # the old mapper integrates into the resized map
     compare_maps(gmap, omap2, layers=["elevation", "elevation_min", "elevation_max", "obstacle"])
 

@@ -132,3 +132,51 @@ def test_sharded_mapper_world_1_equals_plain_mapper(fdem, tmp_path):
     for name in m.getLayers():
         x, y = sm.map.get(name), m.get(name)
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), name
+
+
+def _inpaint_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl = syn.WORKLOADS["tiny"]
+        cfg = wl.config()
+        cfg.mode = capi.MODE_GLOBAL
+        sm = sharded.ShardedGlobalMap(wl.map_width, wl.map_height, wl.resolution, cfg, device=0)
+        for k in range(4):
+            s = syn.make_scan(wl, k)
+            if rank == 0:
+                sm.integrate(s["xyzw"], s["intensity"], s["rgb"], s["T_base_sensor"], s["T_world_base"], src=0)
+            else:
+                sm.integrate(src=0)
+        inp = sm.inpaint(3, 2)          # CUDA stencil on the stripe, halo rows exchanged between sweeps
+        np.save(os.path.join(out_dir, f"inp{rank}.npy"), inp)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_sharded_inpainting_runs_the_cuda_stencil_with_halo_rows(fdem, tmp_path):
+    """applyInpainting over row stripes: fdem_inpaint_stripe_sweep per stripe, one halo row to /
+    from each neighbour between sweeps (device tensors under NCCL; here two processes on one GPU
+    with a gloo group).  The stripes must concatenate to the oracle's whole-map result."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_inpaint_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / f"inp{r}.npy") for r in range(world)], axis=0)
+    wl = syn.WORKLOADS["tiny"]
+    cfg = wl.config()
+    cfg.mode = capi.MODE_GLOBAL
+    m = ob.OracleMap(wl.map_width, wl.map_height, wl.resolution)
+    d = ob.OracleFastDEM(m, cfg)
+    for k in range(4):
+        s = syn.make_scan(wl, k)
+        d.integrate(s["xyzw"], s["T_base_sensor"], s["T_world_base"], s["intensity"], s["rgb"])
+    m.inpaint(3, 2, False)
+    want = m.get("elevation_inpainted")
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=1e-6, atol=0)
+    assert np.isfinite(want).sum() > np.isfinite(m.get("elevation")).sum()

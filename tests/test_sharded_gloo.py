@@ -50,6 +50,40 @@ class OracleStripe:
     def is_empty(self):
         return bool(np.isnan(self.get("elevation")).all())
 
+    # stencil interface of a stripe engine (the CUDA engine runs fdem_inpaint_stripe_sweep)
+    def inpaint_begin(self):
+        self._inp = np.asarray(self.get("elevation"), np.float32).copy()
+
+    def border_rows(self, name):
+        return torch.from_numpy(self._inp[0].copy()), torch.from_numpy(self._inp[-1].copy())
+
+    def inpaint_sweep(self, name, above, below, min_valid):
+        cur = self._inp
+        R, cols = cur.shape
+        padded = np.full((R + 2, cols + 2), np.nan, np.float32)
+        padded[1:-1, 1:-1] = cur
+        if above is not None:
+            padded[0, 1:-1] = above.numpy()
+        if below is not None:
+            padded[-1, 1:-1] = below.numpy()
+        total = np.zeros((R, cols), np.float32)
+        count = np.zeros((R, cols), np.int32)
+        for dr in (-1, 0, 1):          # the oracle's neighbour order: dr outer, dc inner
+            for dc in (-1, 0, 1):
+                if dr == 0 and dc == 0:
+                    continue
+                nb = padded[1 + dr: 1 + dr + R, 1 + dc: 1 + dc + cols]
+                ok = np.isfinite(nb)
+                total = np.where(ok, total + np.where(ok, nb, np.float32(0)), total).astype(np.float32)
+                count += ok
+        fill = np.isnan(cur) & (count >= min_valid)
+        nxt = cur.copy()
+        nxt[fill] = (total[fill] / count[fill].astype(np.float32)).astype(np.float32)
+        self._inp = nxt
+
+    def result(self, name):
+        return self._inp
+
 
 def _global_cfg():
     wl = syn.WORKLOADS["tiny"]
