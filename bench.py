@@ -36,6 +36,7 @@ not shard.  The line then also carries the same-box one-GPU C5 
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -864,6 +865,9 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host thread (and with it the pinned buffers it first-touches) onto the GPU's NUMA node
+    ncpu = ctypes.c_int32(0)
+    numa_bound = fd.load_library().fdem_bind_thread_to_device(local_rank, ctypes.byref(ncpu)) == 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -903,6 +907,7 @@ def main():
             if k in res:
                 out[k] = res[k]
         out["clocks"] = clocks
+        out["host"] = {"cpus": os.cpu_count(), "numa_bound_to_gpu_node": bool(numa_bound), "cpus_in_affinity": int(ncpu.value)}
         if configs is not None:
             out["configs"] = configs
         emit(out)

@@ -138,6 +138,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "fdem_map_pointcloud2_field": (_ST, [_P, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_uint32)]),
     "fdem_map_pointcloud2_data": (_ST, [_P, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdem_bind_thread_to_device": (_ST, [C.c_int32, C.POINTER(C.c_int32)]),
     "fdem_device_alloc": (_ST, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
     "fdem_device_free": (_ST, [C.c_int32, C.c_void_p]),
     "fdem_ipc_export": (_ST, [C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(FdemIpcHandle)]),

@@ -3,8 +3,10 @@
 // map state happens in kernels.cu / kernels_raycast.cu.  There is no CPU fallback: every
 // entry point needs a working CUDA device.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>

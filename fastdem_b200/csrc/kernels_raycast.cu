@@ -149,9 +149,12 @@ voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restri
                          uint32_t* __restrict__ ray_hist) {
   __shared__ uint32_t s_warp[kBlock / 32];
   __shared__ uint32_t s_base;
+  __shared__ uint32_t s_len[kRayLenBins];   // rays per length bin of this block (one global atomic per bin)
   const GridGeom g = st->geom;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < kRayLenBins) s_len[threadIdx.x] = 0u;
+  __syncthreads();
   // preconditions (raycasting.cpp:230-234): sensor origin must be inside the map; the voxel
   // count is still reported (voxelGrid runs before applyRaycasting, fastdem.cpp:156-158)
   const bool rc_ok = geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]));
@@ -207,7 +210,7 @@ voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restri
         const uint32_t okey = static_cast<uint32_t>(lenbin * kRayAzBins + azbin);
         pt.w = __uint_as_float(okey);
         atomicAdd(&ray_hist[okey], 1u);
-        atomicAdd(&ray_hist[2 * kRayBins + lenbin], 1u);   // rays per length bin (segment bases)
+        atomicAdd(&s_len[lenbin], 1u);   // rays per length bin (segment bases)
       }
     }
   }
@@ -228,6 +231,7 @@ voxel_select_rays_kernel(const Key* __restrict__ skeys, const uint32_t* __restri
     if (skeys && heads_total) atomicAdd(&counters[CNT_VOXELS], heads_total);
     s_base = rays_total ? atomicAdd(&counters[CNT_RAYS], rays_total) : 0u;
   }
+  if (threadIdx.x < kRayLenBins && s_len[threadIdx.x]) atomicAdd(&ray_hist[2 * kRayBins + threadIdx.x], s_len[threadIdx.x]);
   __syncthreads();
   if (trace) rays_unsorted[s_base + s_warp[warp] + __popc(tm & ((1u << lane) - 1u))] = pt;
 }
@@ -1231,14 +1235,20 @@ void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const flo
   static int near = -1;
   if (near < 0) {
     const char* e = std::getenv("FDEM_RAY_NEAR");
-    near = e ? std::atoi(e) : 96;
-    if (near != 64 && near != 96 && near != 128) near = 96;
+    near = e ? std::atoi(e) : 64;
+    if (near != 64 && near != 96 && near != 128) near = 64;
   }
   const uint32_t chunks = (n_max + 31) / 32;  // warps fetch 32 rays at a time
   auto launch = [&](auto kernel, int kn, uint32_t ctas_per_sm) {
     const size_t smem = sizeof(uint32_t) * kn * kn;
-    // opt-in to > 48 KiB of dynamic shared memory (per device, so not cached in a static)
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    // opt-in to > 48 KiB of dynamic shared memory (a per-device attribute: set once per device)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     static const int ctas_env = [] { const char* e = std::getenv("FDEM_RAY_CTAS"); return e ? std::atoi(e) : 0; }();
     if (ctas_env > 0 && static_cast<uint32_t>(ctas_env) < ctas_per_sm) ctas_per_sm = static_cast<uint32_t>(ctas_env);
     const uint32_t want = (chunks + (kBlock / 32) - 1) / (kBlock / 32) * 4u;   // ~4 segment tasks per bundle

@@ -130,7 +130,7 @@ class ElevationMap {
   // work through this proxy (the cell lives in HBM; a read or a write is one small transfer)
   class CellRef {
    public:
-    operator float() const { return map_->at(static_cast<const std::string&>(name_), idx_); }
+    operator float() const { return static_cast<const ElevationMap*>(map_)->at(name_, idx_); }  // the const overload: a read
     CellRef& operator=(float v) { map_->setAt(name_, idx_, v); return *this; }
     CellRef& operator=(const CellRef& o) { return *this = static_cast<float>(o); }
     CellRef& operator+=(float v) { return *this = static_cast<float>(*this) + v; }
@@ -139,7 +139,6 @@ class ElevationMap {
    private:
     friend class ElevationMap;
     CellRef(ElevationMap* m, std::string n, nanogrid::Index i) : map_(m), name_(std::move(n)), idx_(i) {}
-    const ElevationMap* cmap() const { return map_; }
     ElevationMap* map_;
     std::string name_;
     nanogrid::Index idx_;

@@ -381,6 +381,11 @@ typedef struct fdem_ipc_handle {
   uint8_t bytes[64]; /* cudaIpcMemHandle_t */
   uint64_t size;
 } fdem_ipc_handle;
+/* Bind the calling host thread to the CPUs local to the device's NUMA node (sysfs
+ * local_cpulist); *n_cpus (may be NULL) = CPUs in the set.  Call it before allocating the pinned
+ * scan buffers: one process per GPU on a multi-socket box otherwise pins everything on node 0.
+ * FDEM_ERR_UNSUPPORTED when the topology is not exposed (containers without sysfs). */
+fdem_status fdem_bind_thread_to_device(int32_t device, int32_t* n_cpus);
 fdem_status fdem_device_alloc(int32_t device, size_t bytes, void** ptr);
 fdem_status fdem_device_free(int32_t device, void* ptr);
 /* `ptr` must come from fdem_device_alloc (IPC handles name whole allocations) */

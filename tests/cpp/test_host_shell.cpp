@@ -159,9 +159,9 @@ int main() {
     const nanogrid::Matrix ea = a.get(layer::elevation), eb = b.get(layer::elevation);
     int finite = 0, larger = 0;
     for (size_t i = 0; i < pa.size(); ++i) {
-      if (!std::isfinite(pa.data()[i])) { EXPECT_TRUE(!std::isfinite(pb.data()[i])); continue; }
+      if (!std::isfinite(ea.data()[i])) { EXPECT_TRUE(!std::isfinite(eb.data()[i])); continue; }  // unobserved cell
       ++finite;
-      EXPECT_TRUE(pa.data()[i] == pb.data()[i] && ea.data()[i] == eb.data()[i]);
+      EXPECT_TRUE(pa.data()[i] == pb.data()[i] && ea.data()[i] == eb.data()[i]);   // bit for bit
       if (pc.data()[i] > pa.data()[i]) ++larger;
     }
     EXPECT_TRUE(finite > 10 && larger > 0);
