@@ -713,6 +713,19 @@ def measure_sharded(cx: Ctx, wl, sampler):
                 sm.integrate_async(clouds[K[0] % n_dev], *pose_of(K[0]))
                 K[0] += 1
 
+        if os.environ.get("FDEM_BENCH_WATCHDOG"):   # debugging aid: the handshake flags if the queue stalls
+            def flags_watchdog():
+                time.sleep(float(os.environ["FDEM_BENCH_WATCHDOG"]) * 0.5)
+                out = (ctypes.c_uint32 * 17)()
+                try:
+                    fn = sm.lib.fdem_shard_debug_flags   # FDEM_PROBES=1 builds only
+                except AttributeError:
+                    return
+                fn.restype, fn.argtypes = ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p]
+                rc = fn(sm._h, out)
+                print(f"[flags rank {rank}] rc={rc} ready={list(out[0:world])} consumed={list(out[8:8 + world])} "
+                      f"seq={out[16]}", file=sys.stderr, flush=True)
+            threading.Thread(target=flags_watchdog, daemon=True).start()
         submit(max(args.warmup, 3))
         sm.wait()
         sampler.wait_first()
@@ -842,6 +855,9 @@ def main():
     ap.add_argument("--no-frame", action="store_true", help="skip the whole-frame (mapping + post-process) block")
     args = ap.parse_args()
 
+    if os.environ.get("FDEM_BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["FDEM_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -801,6 +801,10 @@ class FastDEM:
         """capi.CELL_SORT_TILE (default) or capi.CELL_SORT_GLOBAL; results are identical."""
         check(self._lib.fdem_mapper_set_cell_sort(self._h, mode))
 
+    def set_voxel_sort(self, mode: int) -> None:
+        """capi.VOXEL_SORT_LIBRARY (default, faster) or capi.VOXEL_SORT_MSD (no library launches); results are identical."""
+        check(self._lib.fdem_mapper_set_voxel_sort(self._h, mode))
+
     def set_stage_timing(self, enabled: bool) -> None:
         check(self._lib.fdem_mapper_set_stage_timing(self._h, 1 if enabled else 0))
 

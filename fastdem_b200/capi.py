@@ -16,6 +16,7 @@ SENSOR_CONSTANT, SENSOR_LIDAR, SENSOR_RGBD = 0, 1, 2
 MODE_LOCAL, MODE_GLOBAL = 0, 1
 EST_KALMAN, EST_P2QUANTILE = 0, 1
 MOVE_CLEAR_ALL_LAYERS, MOVE_CLEAR_BASIC_LAYERS = 0, 1
+VOXEL_SORT_MSD, VOXEL_SORT_LIBRARY = 0, 1
 CELL_SORT_TILE, CELL_SORT_GLOBAL = 0, 1
 STAGE_NAMES = ["h2d", "preprocess_bin", "commit_move_clear", "sort_by_cell", "segreduce_estimate",
                "voxel_raycast"]
@@ -156,6 +157,7 @@ SIGNATURES = {
     "fdem_mapper_library_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),
     "fdem_mapper_set_stage_timing": (_ST, [_P, C.c_int32]),
     "fdem_mapper_set_cell_sort": (_ST, [_P, C.c_int32]),
+    "fdem_mapper_set_voxel_sort": (_ST, [_P, C.c_int32]),
     "fdem_mapper_stage_times": (_ST, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

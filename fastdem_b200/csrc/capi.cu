@@ -148,7 +148,9 @@ struct ScanLaunch {
   uint32_t* host_out;
   PublishArgs pub;
 };
-enum { GN_K1 = 0, GN_K2, GN_SCATTER, GN_K3T, GN_COUNT };
+// GN_K3L (the warp-per-bucket pass of K3t) is part of the chain only when the scan shape is
+// "light" (TileBuffers::job_counter == CNT_HEAVY)
+enum { GN_K1 = 0, GN_K2, GN_SCATTER, GN_K3L, GN_K3T, GN_COUNT };
 struct ScanGraph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -181,6 +183,9 @@ struct fdem_mapper {
   float4* d_rays = nullptr;                          // rays to trace (end points), (length, azimuth) bundles
   float4* d_rays_tmp = nullptr;                      // the same in discovery order
   uint32_t* d_ray_hist = nullptr;                    // counting-sort histogram + cursors
+  uint32_t* d_vox_rows = nullptr;                    // MSD voxel sort: row tables (voxel_rows_scratch_words)
+  uint32_t vox_rows_cap = 0;
+  bool voxel_sort_library = true;                    // false: the 2-level MSD sort of kernels_raycast.cu
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_geom = nullptr, ev_rays = nullptr;
   void* d_sort_temp = nullptr;
@@ -202,6 +207,8 @@ struct fdem_mapper {
   TileBuffers tb{};
   uint32_t max_buckets = 0;   // bucket arrays are sized for the smallest bucket shape
   bool bucket_bits_auto = true;  // pick the K3t bucket shape from the last scan's density
+  bool tile_light_auto = true;   // ... and whether the warp-per-bucket pass runs first
+  bool tile_light_pin = false;   // FDEM_TILE_LIGHT=1: always, where the bucket shape allows it
   // batched integration (fdem_mapper_integrate_batch): a second scratch set so scan k+1's
   // front half can run beside scan k's estimator, a ring of state slots, the batch graph
   float4* d_pm2 = nullptr;
@@ -432,6 +439,9 @@ void free_scratch(fdem_mapper* mp) {
   cudaFree(mp->d_rays);
   cudaFree(mp->d_rays_tmp);
   cudaFree(mp->d_ray_hist);
+  cudaFree(mp->d_vox_rows);
+  mp->d_vox_rows = nullptr;
+  mp->vox_rows_cap = 0;
   mp->d_vk32 = mp->d_svk32 = mp->d_vv = mp->d_svv = nullptr;
   mp->d_rays = mp->d_rays_tmp = nullptr;
   mp->d_ray_hist = nullptr;
@@ -851,7 +861,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
     // K1 -> K2 -> scatter -> K3t -> publish as one cudaGraphLaunch; only the nodes whose
     // arguments changed since the last scan are patched
     launch_status = launch_scan_graph(mp, s);
-    m->lc.mine += GN_COUNT;
+    m->lc.mine += mp->tb.job_counter == CNT_HEAVY ? GN_COUNT : GN_COUNT - 1;
   } else {
     mark(FDEM_STAGE_PREPROCESS);
     launch_preprocess_bin(pp, st_in, mp->d_counters, mp->d_pm, mp->d_keys, mp->d_vals, s, m->lc);
@@ -883,7 +893,24 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
       VoxelBox box{};
       cudaError_t se = cudaSuccess;
       const RaySortScratch rss{mp->d_ray_hist, mp->d_rays_tmp, mp->d_rays};
-      if (voxel_box(cfg, pp.T2, voxel, &box)) {
+      const bool have_box = voxel_box(cfg, pp.T2, voxel, &box);
+      if (have_box && !mp->voxel_sort_library && box.by + box.bz <= 22) {
+        // our own 2-level MSD sort (rows = (z, y), then x on chip): no library launches
+        const uint32_t n_rows = 1u << (box.by + box.bz);
+        if (mp->vox_rows_cap < n_rows) {
+          FDEM_CUDA_TRY(cudaStreamSynchronize(aux));
+          cudaFree(mp->d_vox_rows);
+          mp->d_vox_rows = nullptr;
+          mp->vox_rows_cap = 0;
+          const size_t words = voxel_rows_scratch_words(n_rows);
+          FDEM_CUDA_TRY(cudaMalloc(&mp->d_vox_rows, words * sizeof(uint32_t)));
+          FDEM_CUDA_TRY(cudaMemset(mp->d_vox_rows, 0, words * sizeof(uint32_t)));
+          mp->vox_rows_cap = n_rows;
+        }
+        const VoxelRowsScratch vs{mp->d_vox_rows, mp->vox_rows_cap, mp->d_vk32,
+                                  reinterpret_cast<unsigned long long*>(mp->d_vkeys)};
+        launch_voxel_select_rays_msd(mp->d_pm, n, 1.0f / voxel, box, vs, rcp, st_out, mp->d_counters, rss, aux, m->lc);
+      } else if (have_box) {
         const int bits = box.bx + box.by + box.bz + 1;
         launch_voxel_keys32(mp->d_pm, n, 1.0f / voxel, box, mp->d_vk32, mp->d_vv, mp->d_counters, aux, m->lc);
         se = sort_pairs_u32(mp->d_sort_temp, mp->sort_temp_bytes, mp->d_vk32, mp->d_svk32,
@@ -913,7 +940,10 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
                                    mp->d_vals, mp->d_svals, n, bits, s, m->lc));
     }
     mark(FDEM_STAGE_ESTIMATE);
-    if (tile) launch_tile_estimate(ep, mp->tb, mp->d_counters, st_out, L.pub, s, m->lc);
+    if (tile) {
+      if (mp->tb.job_counter == CNT_HEAVY) launch_tile_estimate_light(ep, mp->tb, mp->d_counters, st_out, s, m->lc);
+      launch_tile_estimate(ep, mp->tb, mp->d_counters, st_out, L.pub, s, m->lc);
+    }
     else launch_segreduce_estimate(ep, mp->d_counters, mp->d_counters, s, m->lc);
     mark(FDEM_STAGE_RAYCAST);
     if (raycast && !rc_beside && launch_status == FDEM_OK) launch_status = raycast_branch();
@@ -963,6 +993,9 @@ void scan_node_args(ScanLaunch& L, uint32_t n, NodeArgs out[GN_COUNT]) {
   out[GN_K2].args[3] = &L.counters; out[GN_K2].args[4] = &L.lt;
   out[GN_SCATTER].d = desc_scatter_records(n);
   out[GN_SCATTER].args[0] = &L.sp;
+  out[GN_K3L].d = desc_tile_estimate_light();
+  out[GN_K3L].args[0] = &L.ep; out[GN_K3L].args[1] = &L.tb; out[GN_K3L].args[2] = &L.counters;
+  out[GN_K3L].args[3] = &L.st_next;
   out[GN_K3T].d = desc_tile_estimate(L.tb.n_buckets, L.tb.bucket_bits);
   out[GN_K3T].args[0] = &L.ep; out[GN_K3T].args[1] = &L.tb; out[GN_K3T].args[2] = &L.counters;
   out[GN_K3T].args[3] = &L.st_next; out[GN_K3T].args[4] = &L.pub;
@@ -990,22 +1023,26 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
   ScanGraph& G = mp->sg;
   NodeArgs na[GN_COUNT];
   scan_node_args(L, L.pp.n, na);
+  const bool light = L.tb.job_counter == CNT_HEAVY;
+  int chain[GN_COUNT], n_chain = 0;
+  for (int i = 0; i < GN_COUNT; ++i)
+    if (i != GN_K3L || light) chain[n_chain++] = i;
   if (!G.valid) {
     destroy_scan_graph(mp);
     FDEM_CUDA_TRY(cudaGraphCreate(&G.graph, 0));
-    for (int i = 0; i < GN_COUNT; ++i) {
-      cudaKernelNodeParams kp = node_params(na[i]);
-      FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i], G.graph, nullptr, 0, &kp));
+    for (int c = 0; c < n_chain; ++c) {
+      cudaKernelNodeParams kp = node_params(na[chain[c]]);
+      FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[chain[c]], G.graph, nullptr, 0, &kp));
     }
-    for (int i = 1; i < GN_COUNT; ++i) {
-      // programmatic edges: node i may launch as soon as node i-1 has called
-      // griddepcontrol.launch_dependents; it blocks at griddepcontrol.wait until i-1 is done
+    for (int c = 1; c < n_chain; ++c) {
+      // programmatic edges: a node may launch as soon as its predecessor has called
+      // griddepcontrol.launch_dependents; it blocks at griddepcontrol.wait until that one is done
       cudaGraphEdgeData ed{};
       if (mp->use_pdl) {
         ed.from_port = cudaGraphKernelNodePortProgrammatic;
         ed.type = cudaGraphDependencyTypeProgrammatic;
       }
-      FDEM_CUDA_TRY(cudaGraphAddDependencies_v2(G.graph, &G.node[i - 1], &G.node[i], &ed, 1));
+      FDEM_CUDA_TRY(cudaGraphAddDependencies_v2(G.graph, &G.node[chain[c - 1]], &G.node[chain[c]], &ed, 1));
     }
     FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
     G.cached = L;
@@ -1021,9 +1058,10 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
     dirty[GN_K2] = shared_changed || std::memcmp(&L.cp, &C.cp, sizeof(L.cp)) != 0 ||
                    std::memcmp(&L.lt, &C.lt, sizeof(L.lt)) != 0;
     dirty[GN_SCATTER] = shared_changed || std::memcmp(&L.sp, &C.sp, sizeof(L.sp)) != 0;
-    dirty[GN_K3T] = shared_changed || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0 ||
-                    std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
-    for (int i = 0; i < GN_COUNT; ++i) {
+    dirty[GN_K3L] = shared_changed || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0;
+    dirty[GN_K3T] = dirty[GN_K3L] || std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
+    for (int c = 0; c < n_chain; ++c) {
+      const int i = chain[c];
       if (!dirty[i]) continue;
       cudaKernelNodeParams kp = node_params(na[i]);
       FDEM_CUDA_TRY(cudaGraphExecKernelNodeSetParams(G.exec, G.node[i], &kp));
@@ -1042,7 +1080,8 @@ fdem_status launch_scan_graph(fdem_mapper* mp, cudaStream_t s) {
 //   K3_i -> BP_{i+1}                           (map layers, touched list)
 //   K3_i -> K1_{i+2}                           (scratch set i & 1 is free again)
 constexpr int kMaxBatch = 16;  // scans per batch graph
-enum { BN_K1 = 0, BN_K2, BN_SC, BN_BP, BN_K3, BN_COUNT };
+// BN_K3L: the warp-per-bucket pass, only in graphs built for the light scan shape
+enum { BN_K1 = 0, BN_K2, BN_SC, BN_BP, BN_K3L, BN_K3, BN_COUNT };
 
 struct BatchScan {
   ScanLaunch L;
@@ -1089,7 +1128,8 @@ fdem_status ensure_batch_scratch(fdem_mapper* mp) {
     FDEM_CUDA_TRY(cudaMemset(mp->d_batch_counters, 0, kMaxBatch * CNT_COUNT * sizeof(uint32_t)));
     const size_t nb = std::max<size_t>(mp->max_buckets, 1) * sizeof(uint32_t);
     cudaFree(mp->tb2.bucket_count); cudaFree(mp->tb2.bucket_offset); cudaFree(mp->tb2.bucket_cursor);
-    cudaFree(mp->tb2.bucket_list);
+    cudaFree(mp->tb2.bucket_list); cudaFree(mp->tb2.heavy_list);
+    FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.heavy_list, nb * 4));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_count, nb));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_offset, nb));
     FDEM_CUDA_TRY(cudaMalloc(&mp->tb2.bucket_cursor, nb));
@@ -1121,6 +1161,7 @@ void retarget_for_batch(fdem_mapper* mp, int i, BatchScan& b) {
   TileBuffers tb = q ? mp->tb2 : mp->tb;
   tb.n_buckets = mp->tb.n_buckets;
   tb.bucket_bits = mp->tb.bucket_bits;
+  tb.job_counter = mp->tb.job_counter;
   float4* pm = q ? mp->d_pm2 : mp->d_pm;
   uint32_t* keys = q ? mp->d_keys2 : mp->d_keys;
   // one counter block per scan of the batch, all zeroed by ONE memset node at the head of the
@@ -1165,6 +1206,9 @@ void batch_node_args(BatchScan& b, NodeArgs out[BN_COUNT]) {
   out[BN_SC].args[0] = &L.sp;
   out[BN_BP].d = desc_back_prologue();
   out[BN_BP].args[0] = &b.bp; out[BN_BP].args[1] = &L.lt;
+  out[BN_K3L].d = desc_tile_estimate_light();
+  out[BN_K3L].args[0] = &L.ep; out[BN_K3L].args[1] = &L.tb; out[BN_K3L].args[2] = &L.counters;
+  out[BN_K3L].args[3] = &L.st_next;
   out[BN_K3].d = desc_tile_estimate(L.tb.n_buckets, L.tb.bucket_bits);
   out[BN_K3].args[0] = &L.ep; out[BN_K3].args[1] = &L.tb; out[BN_K3].args[2] = &L.counters;
   out[BN_K3].args[3] = &L.st_next; out[BN_K3].args[4] = &L.pub;
@@ -1172,7 +1216,12 @@ void batch_node_args(BatchScan& b, NodeArgs out[BN_COUNT]) {
 
 fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
   BatchGraphState& G = mp->bg[mp->bg_flip];
-  const bool rebuild = !G.exec || G.S != S || G.tile_shape_key != mp->tb.bucket_bits;
+  const bool light = mp->tb.job_counter == CNT_HEAVY;
+  const uint32_t shape_key = mp->tb.bucket_bits | (light ? 0x100u : 0u);
+  const bool rebuild = !G.exec || G.S != S || G.tile_shape_key != shape_key;
+  int chain[BN_COUNT], n_chain = 0;
+  for (int k = 0; k < BN_COUNT; ++k)
+    if (k != BN_K3L || light) chain[n_chain++] = k;
   if (rebuild) {
     if (G.exec) cudaGraphExecDestroy(G.exec);
     if (G.graph) cudaGraphDestroy(G.graph);
@@ -1190,9 +1239,9 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
     for (int i = 0; i < S; ++i) {
       NodeArgs na[BN_COUNT];
       batch_node_args(G.scan[i], na);
-      for (int k = 0; k < BN_COUNT; ++k) {
-        cudaKernelNodeParams kp = node_params(na[k]);
-        FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i][k], G.graph, nullptr, 0, &kp));
+      for (int c = 0; c < n_chain; ++c) {
+        cudaKernelNodeParams kp = node_params(na[chain[c]]);
+        FDEM_CUDA_TRY(cudaGraphAddKernelNode(&G.node[i][chain[c]], G.graph, nullptr, 0, &kp));
       }
     }
     FDEM_CUDA_TRY(cudaGraphAddDependencies(G.graph, &G.zero, &G.node[0][BN_K1], 1));
@@ -1211,9 +1260,10 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
       return cudaGraphAddDependencies_v2(G.graph, &a, &b, &ed, 1);
     };
     for (int i = 0; i < S; ++i) {
-      for (int k = 1; k < BN_COUNT; ++k) {
-        if (k == BN_K3) FDEM_CUDA_TRY(pedge(G.node[i][k - 1], G.node[i][k]));
-        else FDEM_CUDA_TRY(edge(G.node[i][k - 1], G.node[i][k]));
+      for (int c = 1; c < n_chain; ++c) {
+        const int k = chain[c];
+        if (k == BN_K3 || k == BN_K3L) FDEM_CUDA_TRY(pedge(G.node[i][chain[c - 1]], G.node[i][k]));
+        else FDEM_CUDA_TRY(edge(G.node[i][chain[c - 1]], G.node[i][k]));
       }
       if (i + 1 < S) {
         FDEM_CUDA_TRY(edge(G.node[i][BN_K2], G.node[i + 1][BN_K1]));
@@ -1231,7 +1281,7 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
     }
     FDEM_CUDA_TRY(cudaGraphInstantiate(&G.exec, G.graph, 0));
     G.S = S;
-    G.tile_shape_key = mp->tb.bucket_bits;
+    G.tile_shape_key = shape_key;
   } else {
     // patch only the nodes whose arguments differ from what the executable graph holds
     for (int i = 0; i < S; ++i) {
@@ -1249,11 +1299,12 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
       dirty[BN_SC] = shared || std::memcmp(&L.sp, &C.sp, sizeof(L.sp)) != 0;
       dirty[BN_BP] = shared || std::memcmp(&b.bp, &c.bp, sizeof(b.bp)) != 0 ||
                      std::memcmp(&L.lt, &C.lt, sizeof(L.lt)) != 0;
-      dirty[BN_K3] = shared || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0 ||
-                     std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
+      dirty[BN_K3L] = shared || std::memcmp(&L.ep, &C.ep, sizeof(L.ep)) != 0;
+      dirty[BN_K3] = dirty[BN_K3L] || std::memcmp(&L.pub, &C.pub, sizeof(L.pub)) != 0;
       NodeArgs na[BN_COUNT];
       batch_node_args(G.scan[i], na);
-      for (int k = 0; k < BN_COUNT; ++k) {
+      for (int c = 0; c < n_chain; ++c) {
+        const int k = chain[c];
         if (!dirty[k]) continue;
         cudaKernelNodeParams kp = node_params(na[k]);
         FDEM_CUDA_TRY(cudaGraphExecKernelNodeSetParams(G.exec, G.node[i][k], &kp));
@@ -1273,15 +1324,32 @@ fdem_status launch_batch_graph(fdem_mapper* mp, int S, cudaStream_t s) {
 // it switches back.  The L1 scratch is all-zero between scans (K3t re-arms what it consumed)
 // and sized for the smallest shape, so switching needs no clearing; in-flight scans keep the
 // shape they were enqueued with.
-void adapt_bucket_shape(fdem_mapper* mp, uint32_t nonempty_buckets) {
-  if (!mp->bucket_bits_auto || !mp->use_tile || nonempty_buckets == 0) return;
+//
+// The other extreme — a scan spread thin over a large map (a LiDAR sweep on a 0.05 m global map:
+// thousands of buckets holding a few dozen cells each) — takes the "light" shape: a first pass
+// handles every bucket with <= 128 records with one WARP (tile_estimate_light_kernel), and the
+// CTA-per-bucket kernel only sees what that pass left over.
+void adapt_bucket_shape(fdem_mapper* mp, uint32_t nonempty_buckets, uint32_t n_cells) {
+  if (!mp->use_tile || nonempty_buckets == 0) return;
   uint32_t bits = mp->tb.bucket_bits;
-  if (bits == 10u && nonempty_buckets < 160u) bits = 8u;
-  else if (bits == 8u && nonempty_buckets > 800u) bits = 10u;
-  if (bits == mp->tb.bucket_bits) return;
+  if (mp->bucket_bits_auto) {
+    if (bits == 10u && nonempty_buckets < 160u) bits = 8u;
+    else if (bits == 8u && nonempty_buckets > 800u) bits = 10u;
+  }
+  bool light = mp->tb.job_counter == CNT_HEAVY;
+  if (mp->tile_light_auto) {
+    const uint32_t cells_per_bucket = n_cells / nonempty_buckets;
+    if (!light && bits == 10u && nonempty_buckets >= 600u && cells_per_bucket <= 64u) light = true;
+    else if (light && (nonempty_buckets < 400u || cells_per_bucket > 96u)) light = false;
+  } else {
+    light = mp->tile_light_pin;
+  }
+  if (bits != 10u) light = false;
+  if (bits == mp->tb.bucket_bits && light == (mp->tb.job_counter == CNT_HEAVY)) return;
   mp->tb.bucket_bits = bits;
   mp->tb.n_buckets = static_cast<uint32_t>((mp->map->cells + (1ull << bits) - 1) >> bits);
-  mp->sg.valid = false;  // K3t's function and grid change: rebuild the scan graph
+  mp->tb.job_counter = light ? CNT_HEAVY : CNT_BUCKETS;
+  mp->sg.valid = false;  // K3t's function, grid and chain change: rebuild the scan graph
 }
 
 fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
@@ -1299,7 +1367,7 @@ fdem_status finish_scan(fdem_mapper* mp, fdem_scan_stats* stats) {
     mp->last.n_voxels = r.counters[CNT_VOXELS];
     mp->last.integrated = r.counters[CNT_KEPT] > 0 ? 1 : 0;
     mp->last.voxel_box_violations = static_cast<int32_t>(r.counters[CNT_VOX_VIOLATION]);
-    adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
+    adapt_bucket_shape(mp, r.counters[CNT_BUCKETS], r.counters[CNT_CELLS]);
   }
   mp->pending = false;
   if (stats) *stats = mp->last;
@@ -1832,8 +1900,9 @@ static fdem_status mapper_resize_for_map(fdem_mapper* mp) {
   destroy_batch_graph(mp);
   for (TileBuffers* tb : {&mp->tb, &mp->tb2}) {
     cudaFree(tb->bucket_count); cudaFree(tb->bucket_offset); cudaFree(tb->bucket_cursor); cudaFree(tb->bucket_list);
+    cudaFree(tb->heavy_list);
     tb->bucket_count = tb->bucket_offset = tb->bucket_cursor = nullptr;
-    tb->bucket_list = nullptr;
+    tb->bucket_list = tb->heavy_list = nullptr;
   }
   // the second scratch set / state ring of batched integration is rebuilt on its next use
   cudaFree(mp->d_ring); mp->d_ring = nullptr;
@@ -1848,6 +1917,7 @@ static fdem_status mapper_resize_for_map(fdem_mapper* mp) {
   FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_offset, nb));
   FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_cursor, nb));
   FDEM_CUDA_TRY(cudaMalloc(&mp->tb.bucket_list, nb * 4));
+  FDEM_CUDA_TRY(cudaMalloc(&mp->tb.heavy_list, nb * 4));
   mp->tile_dirty = true;
   mp->counters_dirty = true;
   mp->cached_epoch = ~0ull;
@@ -1898,6 +1968,11 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
     mp->use_graph = !(genv && std::string(genv) == "0");
     const char* penv = std::getenv("FDEM_PDL");
     mp->use_pdl = penv && std::string(penv) == "1";  // measured: no gain inside a graph; opt-in
+    const char* venv = std::getenv("FDEM_VOXEL_SORT");
+    // measured on B200 (profiles/, r2): cub's onesweep sorts the 32-bit voxel keys of a 1M-point
+    // scan in 72 us; our MSD sort is exact but its CTA-per-row level costs 150 us on the rows a
+    // dense scan crowds.  The library sort stays the default; FDEM_VOXEL_SORT=msd selects ours.
+    mp->voxel_sort_library = !(venv && std::string(venv) == "msd");
     // K3t bucket shape (kernels_tile.cu): 1024-cell buckets to start with; after every scan
     // whose statistics the host has seen the shape follows the scan's density (set_bucket_bits
     // below).  FDEM_BUCKET_BITS=8|9|10 pins it.
@@ -1908,6 +1983,14 @@ fdem_status fdem_mapper_create(fdem_map* map, const fdem_config* cfg, fdem_mappe
       if (v >= 8 && v <= 10) { bits = static_cast<uint32_t>(v); mp->bucket_bits_auto = false; }
     }
     mp->tb.bucket_bits = bits;
+    // FDEM_TILE_LIGHT=0|1 pins the warp-per-bucket pass off / on (1024-cell buckets only)
+    const char* lenv = std::getenv("FDEM_TILE_LIGHT");
+    mp->tb.job_counter = CNT_BUCKETS;
+    if (lenv && (lenv[0] == '0' || lenv[0] == '1')) {
+      mp->tile_light_auto = false;
+      mp->tile_light_pin = lenv[0] == '1';
+      if (mp->tile_light_pin && bits == 10u) mp->tb.job_counter = CNT_HEAVY;
+    }
     mp->device = map->device;
     cudaError_t e2 = static_cast<cudaError_t>(tile_estimate_configure());
     if (e2 != cudaSuccess) {
@@ -1949,6 +2032,7 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   cudaFree(mp->tb2.bucket_offset);
   cudaFree(mp->tb2.bucket_cursor);
   cudaFree(mp->tb2.bucket_list);
+  cudaFree(mp->tb2.heavy_list);
   cudaFree(mp->d_ring);
   cudaFree(mp->d_move);
   cudaFree(mp->d_batch_counters);
@@ -1961,6 +2045,7 @@ fdem_status fdem_mapper_destroy(fdem_mapper* mp) {
   cudaFree(mp->tb.bucket_offset);
   cudaFree(mp->tb.bucket_cursor);
   cudaFree(mp->tb.bucket_list);
+  cudaFree(mp->tb.heavy_list);
   drain_stage_events(mp);
   for (cudaEvent_t e : mp->ev_pool) cudaEventDestroy(e);
   delete mp;
@@ -2145,7 +2230,7 @@ fdem_status fdem_mapper_collect(fdem_mapper* mp, uint64_t ticket, fdem_scan_stat
     m->geom_stale = false;
     apply_state_flags(m, r.state.flags);
   }
-  adapt_bucket_shape(mp, r.counters[CNT_BUCKETS]);
+  adapt_bucket_shape(mp, r.counters[CNT_BUCKETS], r.counters[CNT_CELLS]);
   return FDEM_OK;
 }
 
@@ -2224,7 +2309,7 @@ fdem_status fdem_mapper_integrate_batch(fdem_mapper* mp, int32_t n_scans, const 
   }
   for (int i = 0; i < n_scans; ++i)
     FDEM_CUDA_TRY(cudaEventRecord(m->ev_scan[(ticket0 + i) % kResultRing], s));
-  m->lc.mine += static_cast<int64_t>(BN_COUNT) * n_scans;
+  m->lc.mine += static_cast<int64_t>(mp->tb.job_counter == CNT_HEAVY ? BN_COUNT : BN_COUNT - 1) * n_scans;
   m->seq = ticket0 + n_scans;
   mp->last_ticket = ticket0 + n_scans - 1;
   m->geom_stale = true;
@@ -2394,6 +2479,17 @@ fdem_status fdem_mapper_set_cell_sort(fdem_mapper* mp, int32_t mode) {
   FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
   mp->use_tile = mode == FDEM_CELL_SORT_TILE;
   mp->tile_dirty = true;
+  return FDEM_OK;
+}
+
+fdem_status fdem_mapper_set_voxel_sort(fdem_mapper* mp, int32_t mode) {
+  FDEM_MAPPER_ALIVE(mp);
+  FDEM_REQUIRE(mp, "null mapper");
+  FDEM_REQUIRE(mode == FDEM_VOXEL_SORT_MSD || mode == FDEM_VOXEL_SORT_LIBRARY, "bad voxel sort mode");
+  DeviceGuard dg(mp->map->device);
+  FDEM_CUDA_TRY(cudaStreamSynchronize(mp->map->stream));
+  if (mp->aux_stream) FDEM_CUDA_TRY(cudaStreamSynchronize(mp->aux_stream));
+  mp->voxel_sort_library = mode == FDEM_VOXEL_SORT_LIBRARY;
   return FDEM_OK;
 }
 

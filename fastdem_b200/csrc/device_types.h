@@ -23,7 +23,8 @@ enum Counter : int {
   CNT_BUCKETS = 9,     // tile path: non-empty buckets this scan
   CNT_WORK = 10,       // tile path: K3t's dynamic work counter
   CNT_RAY_WORK = 11,   // raycasting: next unfetched ray bundle
-  CNT_COUNT = 12
+  CNT_HEAVY = 12,      // tile path: buckets the warp-per-bucket kernel left to the CTA-per-bucket kernel
+  CNT_COUNT = 16
 };
 
 // ── tile path: 2-level sort-by-cell ───────────────────────────────────────────
@@ -50,6 +51,10 @@ struct TileBuffers {
   CellRecord* records;      // [capacity in points]
   uint32_t n_buckets;
   uint32_t bucket_bits;     // cells per bucket = 1 << bucket_bits
+  // K3t's work list: bucket_list with counters[CNT_BUCKETS] entries (K2), or — after the light
+  // pass has taken the small buckets — heavy_list with counters[CNT_HEAVY] entries
+  uint4* heavy_list;        // [n_buckets]
+  uint32_t job_counter;     // CNT_BUCKETS (0 means that too) or CNT_HEAVY
 };
 
 // State that survives from scan to scan and is decided on the device (so a stream of
@@ -136,6 +141,8 @@ struct ShardBackArgs {               // owner side
   const uint32_t* peer_offset[kMaxShards];     // source s's first record slot per bucket
   const CellRecord* peer_records[kMaxShards];  // source s's record buffer, this scan's parity
   ShardJob* jobs;                              // [buckets per stripe]
+  ShardJob* heavy_jobs;                        // [buckets per stripe] left over by the light pass
+  uint32_t job_counter;                        // which counter holds the length of the list K3t walks
   uint32_t seq;
   int32_t world, rank;
   uint32_t bps;                                // buckets per stripe (= stride >> 10)
@@ -339,6 +346,13 @@ KernelDesc desc_back_prologue();
 KernelDesc desc_publish();
 KernelDesc desc_scatter_records(uint32_t n);
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits);
+KernelDesc desc_shard_begin();
+KernelDesc desc_shard_alloc();
+KernelDesc desc_shard_publish_front();
+KernelDesc desc_shard_gather();
+KernelDesc desc_tile_estimate_shard(uint32_t bps);
+KernelDesc desc_tile_estimate_light();
+KernelDesc desc_tile_estimate_light_shard();
 // tile path (kernels_tile.cu)
 void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounter& lc);
 void launch_tile_estimate(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
@@ -356,6 +370,11 @@ void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t 
 void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
                                 LaunchCounter& lc);
 void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+// light pass of K3t: one warp per bucket with <= 128 records; bigger buckets go to the heavy list
+void launch_tile_estimate_light(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
+                                DeviceState* st_out, cudaStream_t s, LaunchCounter& lc);
+void launch_tile_estimate_light_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
+                                      DeviceState* st_out, cudaStream_t s, LaunchCounter& lc);
 void launch_tile_estimate_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
                                 DeviceState* st_out, const PublishArgs& pub, cudaStream_t s,
                                 LaunchCounter& lc);
@@ -396,6 +415,18 @@ void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sor
                                 const RaycastParams& p, const DeviceState* st, const float4* pts,
                                 uint32_t* counters, const RaySortScratch& rs, cudaStream_t s,
                                 LaunchCounter& lc);
+// scratch of the MSD voxel sort: `words` holds 5 row-sized arrays + 2 block-sized + 8 control words
+// (voxel_rows_scratch_words(rows_cap)), all zero when first used and re-armed by the kernels
+struct VoxelRowsScratch {
+  uint32_t* words;
+  uint32_t rows_cap;            // rows the arrays were sized for (a power of two, >= 1 << (by + bz))
+  uint32_t* vkey;               // [n]
+  unsigned long long* pairs;    // [n]
+};
+size_t voxel_rows_scratch_words(uint32_t rows_cap);
+void launch_voxel_select_rays_msd(const float4* pm, uint32_t n, float inv_voxel, const VoxelBox& box,
+                                  const VoxelRowsScratch& vs, const RaycastParams& p, const DeviceState* st,
+                                  uint32_t* counters, const RaySortScratch& rs, cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
                         uint32_t n_max, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 void launch_raycast_resolve(const RaycastParams& p, const DeviceState* st, const LayerTable& lt,

@@ -280,6 +280,372 @@ ray_bin_scatter_kernel(const float4* __restrict__ rays_unsorted, float4* __restr
   }
 }
 
+// ═════════════ voxelGrid(ANY) without a library sort: a 2-level MSD sort built for it ═════════════
+// The voxel key is [z][y][x]; what voxelGrid needs from the sort is, per voxel, its point count,
+// its global rank `start` among the valid points, and its points in index order
+// (voxel_grid_impl.hpp:63,171-172).  Level 1 partitions the points by ROW = (z, y) — a 5 cm x
+// 5 cm strip along x — with one histogram pass, one scan over the rows and one scatter; rows are
+// in key order, so a row's base in the scan IS the global rank of its first point.  Level 2 sorts
+// every row by (x, index) on chip: a row of <= 32 points in the registers of one warp (bitonic
+// over shuffles, no barrier), a bigger row in the shared memory of one CTA (rows beyond its
+// capacity: the same network in global memory — slow but exact).  The representative choice and
+// everything after it (hits, ray list) is fused behind the sort exactly as in
+// voxel_select_rays_kernel.  ~6 short kernels of our own instead of 7 library launches moving
+// 8-byte pairs four times through HBM.
+constexpr int kRowBlock = 1024;          // rows scanned per CTA of the row-scan kernel
+constexpr int kBigRowSmem = 4096;        // pairs a CTA sorts in shared memory
+
+struct VoxelRows {
+  uint32_t* row_count;    // [n_rows] points per row; all zero between scans
+  uint32_t* row_excl;     // [n_rows] exclusive prefix inside the row's block of kRowBlock rows
+  uint32_t* row_cursor;   // [n_rows] scatter cursors
+  uint32_t* block_sum;    // [n_blocks]
+  uint32_t* block_base;   // [n_blocks] exclusive prefix over the blocks
+  uint32_t* small_list;   // [n_rows] rows with 1..32 points
+  uint32_t* big_list;     // [n_rows] rows with more
+  uint32_t* ctl;          // [8]: 0 n_small, 1 n_big, 2 ticket, 3 small work, 4 big work
+  uint32_t* vkey;         // [n] voxel key per point (invalid_key: dropped)
+  unsigned long long* pairs;  // [n] (x << 32 | point index), grouped by row
+  uint32_t n_rows, n_blocks, bx, invalid_key;
+};
+
+// level 1a: key per point + rows histogram.  Consecutive points of a scan line often fall into
+// the same row: one atomic per run of equal rows in a warp.
+__global__ void __launch_bounds__(kBlock)
+voxel_rows_kernel(const float4* __restrict__ pm, uint32_t n, float inv, const VoxelBox box,
+                  const __grid_constant__ VoxelRows vr, uint32_t* __restrict__ counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (i < 8) vr.ctl[i] = 0u;   // lists and work counters of this scan (the previous scan's consumers are done)
+  uint32_t key = box.invalid_key;
+  if (i < n) {
+    const float4 q = __ldg(&pm[i]);
+    if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+      constexpr int32_t OFF = 1 << 20;
+      int32_t ix = static_cast<int32_t>(floorf(q.x * inv));
+      int32_t iy = static_cast<int32_t>(floorf(q.y * inv));
+      int32_t iz = static_cast<int32_t>(floorf(q.z * inv));
+      ix = min(max(ix, -OFF), OFF - 1) - box.x0;
+      iy = min(max(iy, -OFF), OFF - 1) - box.y0;
+      iz = min(max(iz, -OFF), OFF - 1) - box.z0;
+      const int32_t mx = (1 << box.bx) - 1, my = (1 << box.by) - 1, mz = (1 << box.bz) - 1;
+      if (ix < 0 || ix > mx || iy < 0 || iy > my || iz < 0 || iz > mz) {
+        atomicAdd(&counters[CNT_VOX_VIOLATION], 1u);   // cannot happen while the transforms are rigid
+        ix = min(max(ix, 0), mx); iy = min(max(iy, 0), my); iz = min(max(iz, 0), mz);
+      }
+      key = (static_cast<uint32_t>(iz) << (box.bx + box.by)) | (static_cast<uint32_t>(iy) << box.bx) |
+            static_cast<uint32_t>(ix);
+    }
+    vr.vkey[i] = key;
+  }
+  const uint32_t row = key == box.invalid_key ? 0xffffffffu : key >> vr.bx;
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+  const bool head = lane == 0 || row != prev;
+  const uint32_t hm = __ballot_sync(0xffffffffu, head);
+  if (head && row != 0xffffffffu) {
+    const uint32_t above = hm & ~((2u << lane) - 1u);           // heads after mine
+    const int end = above ? __ffs(above) - 1 : 32;
+    atomicAdd(&vr.row_count[row], static_cast<uint32_t>(end - lane));
+  }
+}
+
+// level 1b: exclusive scan over the rows (per block of kRowBlock rows + the last block to finish
+// scans the block totals), the two work lists, and the re-arming of the histogram
+__global__ void __launch_bounds__(kBlock)
+voxel_row_scan_kernel(const __grid_constant__ VoxelRows vr) {
+  __shared__ uint32_t s_warp[kBlock / 32];
+  __shared__ uint32_t s_small[kRowBlock], s_big[kRowBlock];
+  __shared__ uint32_t s_ns, s_nb, s_bs, s_bb, s_last;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) { s_ns = 0; s_nb = 0; }
+  __syncthreads();
+  constexpr int PER = kRowBlock / kBlock;   // 4 consecutive rows per thread
+  const uint32_t r0 = blockIdx.x * kRowBlock + t * PER;
+  uint32_t c[PER];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    c[k] = (r0 + k < vr.n_rows) ? vr.row_count[r0 + k] : 0u;
+    sum += c[k];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t wprefix = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) {
+    if (w < warp) wprefix += s_warp[w];
+    total += s_warp[w];
+  }
+  uint32_t base = wprefix + inc - sum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    if (r0 + k < vr.n_rows) {
+      vr.row_excl[r0 + k] = base;
+      vr.row_cursor[r0 + k] = 0u;
+      if (c[k]) {
+        vr.row_count[r0 + k] = 0u;   // re-arm (rows that stayed empty are zero already)
+        if (c[k] <= 32u) s_small[atomicAdd(&s_ns, 1u)] = r0 + k;
+        else s_big[atomicAdd(&s_nb, 1u)] = r0 + k;
+      }
+    }
+    base += c[k];
+  }
+  __syncthreads();
+  if (t == 0) {
+    s_bs = s_ns ? atomicAdd(&vr.ctl[0], s_ns) : 0u;
+    s_bb = s_nb ? atomicAdd(&vr.ctl[1], s_nb) : 0u;
+    vr.block_sum[blockIdx.x] = total;
+    __threadfence();
+    s_last = (atomicAdd(&vr.ctl[2], 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  // lists keep (row, count): the consumers need both
+  for (uint32_t k = t; k < s_ns; k += kBlock) vr.small_list[s_bs + k] = s_small[k];
+  for (uint32_t k = t; k < s_nb; k += kBlock) vr.big_list[s_bb + k] = s_big[k];
+  if (s_last) {
+    // exclusive scan of the block totals (n_blocks <= a few thousand): this CTA, PER per thread in rounds
+    __threadfence();
+    __shared__ uint32_t s_run;
+    if (t == 0) s_run = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < vr.n_blocks; b0 += kBlock) {
+      const uint32_t b = b0 + t;
+      const uint32_t v = b < vr.n_blocks ? __ldcg(&vr.block_sum[b]) : 0u;
+      uint32_t in2 = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, in2, d);
+        if (lane >= d) in2 += o;
+      }
+      if (lane == 31) s_warp[warp] = in2;
+      __syncthreads();
+      uint32_t wp = 0, all = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) {
+        if (w < warp) wp += s_warp[w];
+        all += s_warp[w];
+      }
+      if (b < vr.n_blocks) vr.block_base[b] = s_run + wp + in2 - v;
+      __syncthreads();
+      if (t == 0) s_run += all;
+      __syncthreads();
+    }
+  }
+}
+
+// level 1c: scatter (x, index) into the row segments
+__global__ void __launch_bounds__(kBlock)
+voxel_scatter_kernel(uint32_t n, const __grid_constant__ VoxelRows vr) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t key = i < n ? vr.vkey[i] : vr.invalid_key;
+  const uint32_t row = key == vr.invalid_key ? 0xffffffffu : key >> vr.bx;
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+  const bool head = lane == 0 || row != prev;
+  const uint32_t hm = __ballot_sync(0xffffffffu, head);
+  const int my_head = 31 - __clz(hm & (0xffffffffu >> (31 - lane)));   // lane 0 is always a head
+  uint32_t base = 0;
+  if (head && row != 0xffffffffu) {
+    const uint32_t above = hm & ~((2u << lane) - 1u);
+    const int end = above ? __ffs(above) - 1 : 32;
+    base = vr.block_base[row / kRowBlock] + vr.row_excl[row] +
+           atomicAdd(&vr.row_cursor[row], static_cast<uint32_t>(end - lane));
+  }
+  base = __shfl_sync(0xffffffffu, base, my_head);
+  if (row != 0xffffffffu)
+    vr.pairs[base + (lane - my_head)] =
+        (static_cast<unsigned long long>(key & ((1u << vr.bx) - 1u)) << 32) | i;
+}
+
+// what follows the sort for one voxel representative (processScan's per-point part,
+// raycasting.cpp:160-174): hit count, ray test, ordering key; returns whether the ray is traced
+__device__ __forceinline__ bool ray_of_representative(const RaycastParams& p, const GridGeom& g, float4& pt,
+                                                      uint32_t* __restrict__ ray_hist, uint32_t* s_len) {
+  int32_t row, col;
+  if (geom_get_index(g, static_cast<double>(pt.x), static_cast<double>(pt.y), row, col))
+    atomicAdd(&p.hits[static_cast<size_t>(col) * g.rows + row], 1u);
+  const float dx = pt.x - p.origin[0];
+  const float dy = pt.y - p.origin[1];
+  const float ray_len_2d = sqrtf(dx * dx + dy * dy);
+  if (!(pt.z < p.origin[2] && ray_len_2d >= 1e-4f)) return false;   // upward / degenerate rays (:173, :52-53)
+  const float l1 = fabsf(dx) + fabsf(dy);
+  const int lenbin = min(static_cast<int>(l1 / static_cast<float>(g.res)) >> 5, kRayLenBins - 1);
+  float a = dy / l1;
+  if (dx < 0.0f) a = 2.0f - a;
+  else if (dy < 0.0f) a = 4.0f + a;
+  const int azbin = (min(max(static_cast<int>(a * (kRayAzBins / 4)), 0), kRayAzBins - 1)) & p.tune_az_mask;
+  const uint32_t okey = static_cast<uint32_t>(lenbin * kRayAzBins + azbin);
+  pt.w = __uint_as_float(okey);
+  atomicAdd(&ray_hist[okey], 1u);
+  atomicAdd(&s_len[lenbin], 1u);
+  return true;
+}
+
+// all-ascending bitonic network: compare-exchange (i, l) always leaves the minimum at the lower
+// index, so virtual +inf padding above the data never moves
+__device__ __forceinline__ unsigned long long warp_bitonic32(unsigned long long v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+    {
+      const int l = lane ^ (k - 1);
+      const unsigned long long o = __shfl_sync(0xffffffffu, v, l);
+      v = (lane < l) ? (o < v ? o : v) : (o > v ? o : v);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      const int l = lane ^ j;
+      const unsigned long long o = __shfl_sync(0xffffffffu, v, l);
+      v = (lane < l) ? (o < v ? o : v) : (o > v ? o : v);
+    }
+  }
+  return v;
+}
+
+// level 2, rows of <= 32 points: one warp per row, sorted in registers
+__global__ void __launch_bounds__(kBlock)
+voxel_rows_small_kernel(const __grid_constant__ VoxelRows vr, const __grid_constant__ RaycastParams p,
+                        const DeviceState* __restrict__ st, const float4* __restrict__ pts,
+                        uint32_t* __restrict__ counters, float4* __restrict__ rays_unsorted,
+                        uint32_t* __restrict__ ray_hist) {
+  __shared__ uint32_t s_len[kRayLenBins];
+  if (threadIdx.x < kRayLenBins) s_len[threadIdx.x] = 0u;
+  __syncthreads();
+  const GridGeom g = st->geom;
+  const int lane = threadIdx.x & 31;
+  const bool rc_ok = geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]));
+  if (!rc_ok && blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_RC_SKIP] = 1;
+  const uint32_t n_jobs = vr.ctl[0];
+  uint32_t voxels = 0;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; job < n_jobs; job += warps) {
+    const uint32_t row = vr.small_list[job];
+    const uint32_t base = vr.block_base[row / kRowBlock] + vr.row_excl[row];
+    const uint32_t c = vr.row_cursor[row];   // == the row's point count after the scatter
+    unsigned long long v = lane < static_cast<int>(c) ? vr.pairs[base + lane] : ~0ull;
+    v = warp_bitonic32(v, lane);
+    const uint32_t x = static_cast<uint32_t>(v >> 32);
+    const uint32_t xp = __shfl_up_sync(0xffffffffu, x, 1);
+    const bool valid = lane < static_cast<int>(c);
+    const bool head = valid && (lane == 0 || x != xp);
+    const uint32_t hm = __ballot_sync(0xffffffffu, head);
+    int sel = lane;
+    if (head) {
+      const uint32_t above = hm & ~((2u << lane) - 1u);
+      const uint64_t count = static_cast<uint64_t>((above ? __ffs(above) - 1 : static_cast<int>(c)) - lane);
+      const uint64_t start = static_cast<uint64_t>(base) + lane;   // global rank among the valid points
+      sel = lane + static_cast<int>(count == 1 ? 0ull : (count * 7ull + start * 13ull) % count);
+    }
+    const uint32_t src = static_cast<uint32_t>(__shfl_sync(0xffffffffu, v, sel) & 0xffffffffull);
+    voxels += __popc(hm);
+    bool trace = false;
+    float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (head && rc_ok) {
+      pt = __ldg(&pts[src]);
+      trace = ray_of_representative(p, g, pt, ray_hist, s_len);
+    }
+    const uint32_t tm = __ballot_sync(0xffffffffu, trace);
+    if (tm) {
+      uint32_t rb = 0;
+      if (lane == 0) rb = atomicAdd(&counters[CNT_RAYS], static_cast<uint32_t>(__popc(tm)));
+      rb = __shfl_sync(0xffffffffu, rb, 0);
+      if (trace) rays_unsorted[rb + __popc(tm & ((1u << lane) - 1u))] = pt;
+    }
+  }
+  if (lane == 0 && voxels) atomicAdd(&counters[CNT_VOXELS], voxels);
+  __syncthreads();
+  if (threadIdx.x < kRayLenBins && s_len[threadIdx.x]) atomicAdd(&ray_hist[2 * kRayBins + threadIdx.x], s_len[threadIdx.x]);
+}
+
+// level 2, bigger rows: one CTA per row, sorted in shared memory (or, beyond kBigRowSmem points,
+// in place in global memory)
+__global__ void __launch_bounds__(kBlock)
+voxel_rows_big_kernel(const __grid_constant__ VoxelRows vr, const __grid_constant__ RaycastParams p,
+                      const DeviceState* __restrict__ st, const float4* __restrict__ pts,
+                      uint32_t* __restrict__ counters, float4* __restrict__ rays_unsorted,
+                      uint32_t* __restrict__ ray_hist) {
+  __shared__ unsigned long long s_pairs[kBigRowSmem];
+  __shared__ uint32_t s_len[kRayLenBins];
+  __shared__ uint32_t s_job;
+  if (threadIdx.x < kRayLenBins) s_len[threadIdx.x] = 0u;
+  const GridGeom g = st->geom;
+  const int lane = threadIdx.x & 31;
+  const bool rc_ok = geom_is_inside(g, static_cast<double>(p.origin[0]), static_cast<double>(p.origin[1]));
+  const uint32_t n_jobs = vr.ctl[1];
+  uint32_t voxels = 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_job = atomicAdd(&vr.ctl[4], 1u);
+    __syncthreads();
+    const uint32_t job = s_job;
+    if (job >= n_jobs) break;
+    const uint32_t row = vr.big_list[job];
+    const uint32_t base = vr.block_base[row / kRowBlock] + vr.row_excl[row];
+    const uint32_t c = vr.row_cursor[row];
+    unsigned long long* data;
+    uint32_t P = 32;
+    while (P < c) P <<= 1;
+    if (c <= kBigRowSmem) {
+      for (uint32_t e = threadIdx.x; e < P; e += kBlock) s_pairs[e] = e < c ? vr.pairs[base + e] : ~0ull;
+      data = s_pairs;
+    } else {
+      data = vr.pairs + base;   // in place; indices >= c are virtual +inf
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t e = threadIdx.x; e < P; e += kBlock) {
+          const uint32_t l = (j == (k >> 1)) ? (e ^ (k - 1)) : (e ^ j);
+          if (l > e && l < c) {   // (e < l < c: both real; padding never moves)
+            const unsigned long long a = data[e], b = data[l];
+            if (b < a) { data[e] = b; data[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // one thread per sorted element: heads pick their voxel's representative
+    for (uint32_t e0 = 0; e0 < c; e0 += kBlock) {
+      const uint32_t e = e0 + threadIdx.x;
+      bool head = false, trace = false;
+      float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (e < c) {
+        const uint32_t x = static_cast<uint32_t>(data[e] >> 32);
+        head = e == 0 || static_cast<uint32_t>(data[e - 1] >> 32) != x;
+        if (head) {
+          uint32_t lo = e + 1;
+          while (lo < c && static_cast<uint32_t>(data[lo] >> 32) == x) ++lo;
+          const uint64_t count = lo - e;
+          const uint64_t start = static_cast<uint64_t>(base) + e;
+          const uint32_t src = static_cast<uint32_t>(
+              data[e + (count == 1 ? 0ull : (count * 7ull + start * 13ull) % count)] & 0xffffffffull);
+          if (rc_ok) {
+            pt = __ldg(&pts[src]);
+            trace = ray_of_representative(p, g, pt, ray_hist, s_len);
+          }
+        }
+      }
+      const uint32_t hm = __ballot_sync(0xffffffffu, head);
+      const uint32_t tm = __ballot_sync(0xffffffffu, trace);
+      voxels += (lane == 0) ? __popc(hm) : 0;
+      if (tm) {
+        uint32_t rb = 0;
+        if (lane == 0) rb = atomicAdd(&counters[CNT_RAYS], static_cast<uint32_t>(__popc(tm)));
+        rb = __shfl_sync(0xffffffffu, rb, 0);
+        if (trace) rays_unsorted[rb + __popc(tm & ((1u << lane) - 1u))] = pt;
+      }
+    }
+  }
+  if (lane == 0 && voxels) atomicAdd(&counters[CNT_VOXELS], voxels);
+  __syncthreads();
+  if (threadIdx.x < kRayLenBins && s_len[threadIdx.x]) atomicAdd(&ray_hist[2 * kRayBins + threadIdx.x], s_len[threadIdx.x]);
+}
+
 constexpr int kRayBatch = 8;
 
 // traceRay (raycasting.cpp:46-139): one thread per traced ray, float32 2-D DDA, expression by
@@ -1227,6 +1593,39 @@ void launch_voxel_select_rays64(const uint64_t* sorted_keys, const uint32_t* sor
       sorted_keys, sorted_vals, n, kInvalidVoxel, p, st, pts, counters, rs.unsorted, rs.hist);
   ++lc.mine;
   launch_ray_bundle_sort(rs, n, counters, s, lc);
+}
+// voxelGrid(ANY) + processScan's per-point part through the MSD sort (no library launches)
+void launch_voxel_select_rays_msd(const float4* pm, uint32_t n, float inv_voxel, const VoxelBox& box,
+                                  const VoxelRowsScratch& vs, const RaycastParams& p, const DeviceState* st,
+                                  uint32_t* counters, const RaySortScratch& rs, cudaStream_t s, LaunchCounter& lc) {
+  if (n == 0) return;
+  VoxelRows vr{};
+  vr.bx = static_cast<uint32_t>(box.bx);
+  vr.n_rows = 1u << (box.by + box.bz);
+  vr.n_blocks = (vr.n_rows + kRowBlock - 1) / kRowBlock;
+  vr.invalid_key = box.invalid_key;
+  uint32_t* w = vs.words;
+  vr.row_count = w;  w += vs.rows_cap;
+  vr.row_excl = w;   w += vs.rows_cap;
+  vr.row_cursor = w; w += vs.rows_cap;
+  vr.small_list = w; w += vs.rows_cap;
+  vr.big_list = w;   w += vs.rows_cap;
+  vr.block_sum = w;  w += vs.rows_cap / kRowBlock + 1;
+  vr.block_base = w; w += vs.rows_cap / kRowBlock + 1;
+  vr.ctl = w;
+  vr.vkey = vs.vkey;
+  vr.pairs = vs.pairs;
+  const uint32_t grid_n = (n + kBlock - 1) / kBlock;
+  voxel_rows_kernel<<<grid_n, kBlock, 0, s>>>(pm, n, inv_voxel, box, vr, counters);
+  voxel_row_scan_kernel<<<vr.n_blocks, kBlock, 0, s>>>(vr);
+  voxel_scatter_kernel<<<grid_n, kBlock, 0, s>>>(n, vr);
+  voxel_rows_big_kernel<<<148 * 4, kBlock, 0, s>>>(vr, p, st, pm, counters, rs.unsorted, rs.hist);
+  voxel_rows_small_kernel<<<148 * 8, kBlock, 0, s>>>(vr, p, st, pm, counters, rs.unsorted, rs.hist);
+  lc.mine += 5;
+  launch_ray_bundle_sort(rs, n, counters, s, lc);
+}
+size_t voxel_rows_scratch_words(uint32_t rows_cap) {
+  return 5 * static_cast<size_t>(rows_cap) + 2 * (static_cast<size_t>(rows_cap) / kRowBlock + 1) + 8;
 }
 void launch_raycast_dda(const RaycastParams& p, const DeviceState* st, const float4* rays,
                         uint32_t n_max, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {

@@ -285,9 +285,13 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
   // the job count and this CTA's first list entry are independent loads: one round trip
   // (the list has one slot per bucket and the grid never exceeds that, so the speculative
   // read is in bounds; it is used only when job < n_jobs, i.e. when this scan wrote it)
-  const uint32_t n_jobs = counters[CNT_BUCKETS];
+  // the work list: K2's bucket list, or what the light pass left over
+  const bool leftovers = (SHARD ? shp->job_counter : tb.job_counter) == CNT_HEAVY;
+  const uint4* __restrict__ job_list = leftovers ? tb.heavy_list : tb.bucket_list;
+  const ShardJob* __restrict__ shard_jobs = SHARD ? (leftovers ? shp->heavy_jobs : shp->jobs) : nullptr;
+  const uint32_t n_jobs = counters[leftovers ? CNT_HEAVY : CNT_BUCKETS];
   uint4 entry_next = make_uint4(0u, 0u, 0u, 0u);
-  if (!SHARD) entry_next = tb.bucket_list[blockIdx.x];
+  if (!SHARD) entry_next = job_list[blockIdx.x];
 
   // static round-robin over the non-empty buckets K2 listed: no work-fetch atomics
   for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -295,7 +299,7 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
     uint32_t b, off = 0, nrec;
     ShardJob J;
     if (SHARD) {
-      J = shp->jobs[job];  // {bucket, records, per-source (first slot, count)}
+      J = shard_jobs[job];  // {bucket, records, per-source (first slot, count)}
       b = J.bucket;
       nrec = J.total;
       if (tid == 0) {
@@ -306,7 +310,7 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
       }
     } else {
       const uint4 entry = entry_next;  // {bucket, first record slot, points, -}
-      if (job + gridDim.x < n_jobs) entry_next = tb.bucket_list[job + gridDim.x];  // prefetch
+      if (job + gridDim.x < n_jobs) entry_next = job_list[job + gridDim.x];  // prefetch
       b = entry.x;
       off = entry.y;
       // Stage the first chunk right away.  The record count is not known yet (it is being
@@ -559,6 +563,204 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
 #endif
 }
 
+// ───────────────────────────── K3t, light pass: one WARP per bucket ──────────────────────
+// A scan spread over a large map (C4, C5, every stripe of the multi-GPU map) fills thousands of
+// buckets with a few dozen cells each.  A CTA per such bucket pays its ~7 us chain of dependent
+// phases — each fenced by a block barrier — for a warp's worth of work, three buckets per SM at a
+// time.  Here a bucket with <= kLightRecs records is one WARP's job: its records go to the warp's
+// private shared-memory stage, a counting sort by cell and the per-cell fold run warp-
+// synchronously (no block barrier), and each lane that heads a cell's run does that cell's Kalman
+// / P2 step.  Eight buckets per CTA, ~24 per SM in flight.  Buckets with more records are handed
+// to the CTA-per-bucket kernel through the heavy list.
+constexpr int kLightRecs = 128;
+constexpr int kLightWarps = 8;
+struct LightWarpSmem {
+  CellRecord stage[kLightRecs];
+  uint32_t bins[1024];          // count -> exclusive offset -> cursor, per cell of the bucket
+  uint8_t perm[kLightRecs];     // sorted position -> index into stage
+  uint8_t hpos[kLightRecs];     // touched cell t -> sorted position of its first record
+};
+
+constexpr size_t kLightSmem = sizeof(LightWarpSmem) * kLightWarps;
+constexpr unsigned kLightGrid = 148u * 3u;
+
+template <bool SHARD>
+__device__ __forceinline__ void
+tile_estimate_light_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __restrict__ counters,
+                         DeviceState* __restrict__ st_out, const ShardBackArgs* shp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  LightWarpSmem& W = reinterpret_cast<LightWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  constexpr int kRounds = kLightRecs / 32;
+  pdl_launch_dependents();
+  for (int i = lane; i < 1024; i += 32) W.bins[i] = 0u;
+  __syncwarp();
+  pdl_wait();  // the bucket segments (or the shard job list) are complete from here on
+  const uint32_t n_jobs = counters[CNT_BUCKETS];
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t cells_done = 0;
+  for (uint32_t job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; job < n_jobs; job += n_warps) {
+    uint32_t b, nrec;
+    uint4 entry = make_uint4(0u, 0u, 0u, 0u);
+    ShardJob J;
+    // ── stage the records: coalesced 32-byte reads.  One GPU: the record count is still being
+    //    loaded, the bucket's POINT count bounds it and the segment has that many slots, so
+    //    min(points, 128) records are read speculatively beside it (one round trip less) ──
+    uint4 lo[kRounds], hi[kRounds];
+    if (SHARD) {
+      J = shp->jobs[job];
+      b = J.bucket;
+      nrec = J.total;
+      if (nrec <= static_cast<uint32_t>(kLightRecs)) {
+#pragma unroll
+        for (int k = 0; k < kRounds; ++k) {
+          const uint32_t r = lane + 32u * k;
+          if (r < nrec) {
+            // a sharded bucket's records lie in up to `world` pieces, local or in a peer's arena
+            const CellRecord* src = nullptr;
+            uint32_t pos = 0;
+#pragma unroll
+            for (int sidx = 0; sidx < kMaxShards; ++sidx) {
+              const uint32_t c = J.cnt[sidx];
+              if (src == nullptr && r < pos + c) src = shp->peer_records[sidx] + J.off[sidx] + (r - pos);
+              pos += c;
+            }
+            lo[k] = __ldcg(reinterpret_cast<const uint4*>(src));
+            hi[k] = __ldcg(reinterpret_cast<const uint4*>(src) + 1);
+          }
+        }
+      }
+    } else {
+      entry = tb.bucket_list[job];   // {bucket, first record slot, points, -}
+      b = entry.x;
+      const uint32_t spec = min(entry.z, static_cast<uint32_t>(kLightRecs));
+#pragma unroll
+      for (int k = 0; k < kRounds; ++k) {
+        const uint32_t r = lane + 32u * k;
+        if (r < spec) {
+          const uint4* src = reinterpret_cast<const uint4*>(tb.records + entry.y + r);
+          lo[k] = __ldcg(src);
+          hi[k] = __ldcg(src + 1);
+        }
+      }
+      nrec = tb.bucket_cursor[b];
+    }
+    if (nrec > static_cast<uint32_t>(kLightRecs)) {   // warp-uniform: the CTA-per-bucket kernel takes it
+      if (lane == 0) {
+        const uint32_t h = atomicAdd(&counters[CNT_HEAVY], 1u);
+        if (SHARD) shp->heavy_jobs[h] = J;
+        else tb.heavy_list[h] = entry;
+      }
+      continue;
+    }
+    // ── counting sort by cell, warp-synchronous ──
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+      const uint32_t r = lane + 32u * k;
+      if (r < nrec) {
+        reinterpret_cast<uint4*>(&W.stage[r])[0] = lo[k];
+        reinterpret_cast<uint4*>(&W.stage[r])[1] = hi[k];
+        atomicAdd(&W.bins[lo[k].x], 1u);   // .x is the record's cell within the bucket
+      }
+    }
+    __syncwarp();
+    {
+      // exclusive scan over the 1024 bins: 32 consecutive bins per lane
+      uint4* my = reinterpret_cast<uint4*>(&W.bins[lane * 32]);
+      uint4 v[8];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q] = my[q];
+        sum += v[q].x + v[q].y + v[q].z + v[q].w;
+      }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      if (sum) {
+        // only the touched cells' bins get their offset: the bins of empty cells stay zero for
+        // good, so re-arming after the bucket costs one store per touched cell
+        uint32_t base = inc - sum;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 e;
+          e.x = v[q].x ? base : 0u; base += v[q].x;
+          e.y = v[q].y ? base : 0u; base += v[q].y;
+          e.z = v[q].z ? base : 0u; base += v[q].z;
+          e.w = v[q].w ? base : 0u; base += v[q].w;
+          my[q] = e;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+      const uint32_t r = lane + 32u * k;
+      if (r < nrec) W.perm[atomicAdd(&W.bins[lo[k].x], 1u)] = static_cast<uint8_t>(r);
+    }
+    __syncwarp();
+    // ── the bucket's touched cells = the heads of the runs of equal cells in sorted order ──
+    uint32_t nt = 0;
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+      const uint32_t pp = lane + 32u * k;
+      bool head = false;
+      if (pp < nrec) {
+        const uint32_t key = W.stage[W.perm[pp]].lkey;
+        head = pp == 0 || W.stage[W.perm[pp - 1]].lkey != key;
+      }
+      const uint32_t hm = __ballot_sync(0xffffffffu, head);
+      if (head) W.hpos[nt + __popc(hm & ((1u << lane) - 1u))] = static_cast<uint8_t>(pp);
+      nt += __popc(hm);
+    }
+    // this bucket's slice of the touched-cell list: ONE atomic per bucket, in flight while the
+    // cells are folded
+    uint32_t lb = 0;
+    if (lane == 0) lb = atomicAdd(&st_out->touched_count, nt);
+    __syncwarp();
+    // re-arm the bins for this warp's next bucket (only the touched cells' bins are non-zero)
+    for (uint32_t t = lane; t < nt; t += 32) W.bins[W.stage[W.perm[W.hpos[t]]].lkey] = 0u;
+    if (!SHARD && lane == 0) {   // re-arm the L1 scratch for the next scan
+      tb.bucket_count[b] = 0;
+      tb.bucket_cursor[b] = 0;
+    }
+    // ── one lane per touched cell: fold its run, then that cell's estimator step ──
+    lb = __shfl_sync(0xffffffffu, lb, 0);
+    const uint32_t key_base = b << 10;
+    for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      if (t < nt) {
+        const uint32_t s0 = W.hpos[t];
+        const uint32_t e0 = t + 1 < nt ? static_cast<uint32_t>(W.hpos[t + 1]) : nrec;
+        const uint32_t key = W.stage[W.perm[s0]].lkey;
+        CellObs a = obs_of(W.stage[W.perm[s0]]);
+        for (uint32_t q = s0 + 1; q < e0; ++q) a = obs_combine(a, obs_of(W.stage[W.perm[q]]));
+        apply_observation(p, key_base + key, a);
+        p.touched_keys[lb + t] = key_base + key;
+        if (p.touched_minz) p.touched_minz[lb + t] = a.mz;
+      }
+    }
+    cells_done += nt;
+    __syncwarp();   // every read of this bucket's stage / perm / hpos precedes the next bucket's writes
+  }
+  if (lane == 0 && cells_done) atomicAdd(&counters[CNT_CELLS], cells_done);
+}
+
+__global__ void __launch_bounds__(kLightWarps * 32, 3)
+tile_estimate_light_kernel(const __grid_constant__ EstimateParams p, const __grid_constant__ TileBuffers tb,
+                           uint32_t* __restrict__ counters, DeviceState* __restrict__ st_out) {
+  tile_estimate_light_body<false>(p, tb, counters, st_out, nullptr);
+}
+__global__ void __launch_bounds__(kLightWarps * 32, 3)
+tile_estimate_light_shard_kernel(const __grid_constant__ EstimateParams p, const __grid_constant__ ShardBackArgs sh,
+                                 uint32_t* __restrict__ counters, DeviceState* __restrict__ st_out) {
+  const TileBuffers none{};
+  tile_estimate_light_body<true>(p, none, counters, st_out, &sh);
+}
+
 template <int BITS>
 __global__ void __launch_bounds__(TileCfg<BITS>::kThr, TileCfg<BITS>::kMinBlocks)
 tile_estimate_kernel(const __grid_constant__ EstimateParams p,
@@ -721,6 +923,12 @@ int tile_estimate_configure() {
   e = cudaFuncSetAttribute(tile_estimate_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(sizeof(TileSmem<10>)));
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(tile_estimate_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(kLightSmem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(tile_estimate_light_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(kLightSmem));
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaFuncSetAttribute(tile_estimate_kernel<10>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(sizeof(TileSmem<10>))));
@@ -748,6 +956,16 @@ void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counter
 }
 void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
   shard_gather_kernel<<<148, 256, 0, s>>>(a, counters);
+  ++lc.mine;
+}
+void launch_tile_estimate_light(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,
+                                DeviceState* st_out, cudaStream_t s, LaunchCounter& lc) {
+  tile_estimate_light_kernel<<<kLightGrid, kLightWarps * 32, kLightSmem, s>>>(p, tb, counters, st_out);
+  ++lc.mine;
+}
+void launch_tile_estimate_light_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
+                                      DeviceState* st_out, cudaStream_t s, LaunchCounter& lc) {
+  tile_estimate_light_shard_kernel<<<kLightGrid, kLightWarps * 32, kLightSmem, s>>>(p, a, counters, st_out);
   ++lc.mine;
 }
 void launch_tile_estimate_shard(const EstimateParams& p, const ShardBackArgs& a, uint32_t* counters,
@@ -782,6 +1000,31 @@ namespace fdem {
 KernelDesc desc_scatter_records(uint32_t n) {
   return KernelDesc{reinterpret_cast<const void*>(&scatter_records_kernel),
                     dim3((n + kThreads - 1) / kThreads), dim3(kThreads), 0};
+}
+KernelDesc desc_shard_begin() {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_begin_kernel), dim3(148), dim3(256), 0};
+}
+KernelDesc desc_shard_alloc() {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_alloc_kernel), dim3(148), dim3(256), 0};
+}
+KernelDesc desc_shard_publish_front() {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_publish_front_kernel), dim3(1), dim3(32), 0};
+}
+KernelDesc desc_shard_gather() {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_gather_kernel), dim3(148), dim3(256), 0};
+}
+KernelDesc desc_tile_estimate_shard(uint32_t bps) {
+  const uint32_t cap = 148u * static_cast<uint32_t>(TileCfg<10>::kMinBlocks);
+  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_shard_kernel), dim3(bps < cap ? bps : cap),
+                    dim3(TileCfg<10>::kThr), sizeof(TileSmem<10>)};
+}
+KernelDesc desc_tile_estimate_light() {
+  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_light_kernel), dim3(kLightGrid),
+                    dim3(kLightWarps * 32), kLightSmem};
+}
+KernelDesc desc_tile_estimate_light_shard() {
+  return KernelDesc{reinterpret_cast<const void*>(&tile_estimate_light_shard_kernel), dim3(kLightGrid),
+                    dim3(kLightWarps * 32), kLightSmem};
 }
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits) {
   if (bucket_bits == 8)

@@ -418,7 +418,9 @@ fdem_status fdem_shard_export(fdem_shard* shard, fdem_ipc_handle* out);
 fdem_status fdem_shard_connect(fdem_shard* shard, const fdem_ipc_handle* handles);
 /* FastDEM::integrate(cloud, T_base_sensor, T_world_base) on the striped map, asynchronous.
  * EVERY rank calls it for every scan, in the same order, with the same scan: xyzw / intensity /
- * rgb address the WHOLE scan (n points) in device memory this rank can read. */
+ * rgb address the WHOLE scan (n points) in device memory this rank can read; the scan must be
+ * complete there when the call is made (the halves run on two streams and are not ordered behind
+ * earlier work of the map's stream) and stay untouched until fdem_shard_wait has returned. */
 fdem_status fdem_shard_integrate(fdem_shard* shard, const float* xyzw, const float* intensity,
                                  const uint8_t* rgb, size_t n, const double T_base_sensor[16],
                                  const double T_world_base[16]);
@@ -448,6 +450,14 @@ fdem_status fdem_mapper_stage_times(fdem_mapper* m, double ms[FDEM_STAGE_COUNT],
  *   GLOBAL one CUB radix sort of the whole scan + warp-segmented reduce (kernels.cu) */
 enum { FDEM_CELL_SORT_TILE = 0, FDEM_CELL_SORT_GLOBAL = 1 };
 fdem_status fdem_mapper_set_cell_sort(fdem_mapper* m, int32_t mode);
+/* Which sort voxelGrid(ANY) uses on the raycasting path (results are identical):
+ *   MSD     2-level sort written for it: rows (z, y) by histogram + scan + scatter, then
+ *           (x, index) inside each row on chip — warp registers / shared memory (kernels_raycast.cu);
+ *           no library launches, slower on dense scans
+ *   LIBRARY (default) cub::DeviceRadixSort on 32-bit box-relative keys (on the reference's 63-bit
+ *           keys when the crop filters give no usable bound on the voxel box) */
+enum { FDEM_VOXEL_SORT_MSD = 0, FDEM_VOXEL_SORT_LIBRARY = 1 };
+fdem_status fdem_mapper_set_voxel_sort(fdem_mapper* m, int32_t mode);
 /* kernels launched through CUB (radix-sort passes) since the map was created */
 fdem_status fdem_mapper_library_launch_count(fdem_mapper* m, int64_t* launches);
 /* number of kernels THIS library launched since the handle was created (bench.py's

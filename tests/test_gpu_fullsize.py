@@ -123,3 +123,27 @@ def test_long_stream_soak_matches_oracle(fdem):
     gdem.wait()
     assert n_cells_gpu == n_cells_cpu > 100000
     compare_maps(gmap, omap)
+
+
+def test_voxel_sorts_agree_bit_for_bit(fdem):
+    """voxelGrid(ANY) through the MSD sort written for it and through cub::DeviceRadixSort: same
+    voxel counts, same representatives — hence identical raycasting layers — on the dense C4 scan
+    (rows of every size: thousands of points near the sensor, single points far out)."""
+    wl = syn.WORKLOADS["c4_dense_raycast"]
+    cfg = wl.config()
+    scans = [syn.make_scan(wl, k) for k in range(3)]
+    maps, stats = [], []
+    for mode in (capi.VOXEL_SORT_MSD, capi.VOXEL_SORT_LIBRARY):
+        m = fdem.ElevationMap(wl.map_width, wl.map_height, wl.resolution)
+        d = fdem.FastDEM(m, cfg)
+        d.set_voxel_sort(mode)
+        st = [d.integrate_stats(fdem.PointCloud(s["xyzw"], s["intensity"], s["rgb"]),
+                                s["T_base_sensor"], s["T_world_base"]) for s in scans]
+        maps.append(m)
+        stats.append(st)
+    for a, b in zip(*stats):
+        assert (a.n_kept, a.n_cells, a.n_voxels) == (b.n_kept, b.n_cells, b.n_voxels)
+        assert a.voxel_box_violations == 0 and a.n_voxels > 100000
+    assert maps[0].getLayers() == maps[1].getLayers()
+    for layer in maps[0].getLayers():
+        assert np.array_equal(_bits(maps[0].get(layer)), _bits(maps[1].get(layer))), layer
