@@ -981,7 +981,7 @@ fdem_status enqueue_scan(fdem_mapper* mp, const ScanInputs& in, ScanLaunch* buil
 // ── CUDA graph of one scan (tile path): explicit kernel nodes, patched in place ─────────
 struct NodeArgs {
   KernelDesc d;
-  void* args[8];
+  void* args[12];
 };
 
 void scan_node_args(ScanLaunch& L, uint32_t n, NodeArgs out[GN_COUNT]) {
@@ -1500,7 +1500,12 @@ static fdem_status map_init(fdem_map* m, void* stream) {
   if (stream) {
     m->stream = static_cast<cudaStream_t>(stream);
   } else {
-    FDEM_CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    // the map's own stream carries everything that writes the map; it gets the highest priority so
+    // that, when a mapper overlaps the next scan's front half on its side stream, the CTAs of the
+    // map-writing kernels are placed first
+    int prio_least = 0, prio_greatest = 0;
+    FDEM_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    FDEM_CUDA_TRY(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prio_greatest));
     m->own_stream = true;
   }
   FDEM_CUDA_TRY(cudaMalloc(&m->d_state, 2 * sizeof(DeviceState)));

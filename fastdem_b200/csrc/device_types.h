@@ -117,7 +117,16 @@ struct ShardHeader {
   uint32_t ready[kMaxShards];        // [s] written by source s: front half of scan #ready[s] is complete
   uint32_t consumed[kMaxShards];     // [d] written by owner d: it has finished reading scan #consumed[d]
   uint32_t inside[2][kMaxShards];    // [scan parity][s]: points of source s's slice inside the map
-  uint32_t _pad[32];
+  uint32_t load[2][kMaxShards];      // [scan parity][d] written by owner d with consumed[d]: cells of its
+                                     // stripe that scan touched (what the slice split two scans later uses)
+  uint32_t _pad[16];
+};
+
+// A rank's slice of the scan for the front half, decided ON THE DEVICE by shard_begin_kernel from
+// the owners' loads of two scans ago (identical on every rank): ranks whose stripe got most of
+// the cells — and so most of the back half — bin fewer points.
+struct ShardSlice {
+  uint32_t begin, count;
 };
 
 // one non-empty bucket of this rank's stripe: where its records lie in every source's arena
@@ -167,6 +176,8 @@ struct PreprocessParams {
   const float* cov9;       // optional caller-provided sensor-frame covariances (N x 9, col-major)
   const float* var_z;      // optional (map-frame input): cloud.covariance(i)(2,2)
   uint32_t n;
+  const ShardSlice* slice;  // multi-GPU front half: bin points [begin, begin + count) of the scan
+                            // (read on the device; n bounds the grid)
   int32_t input_frame;
   float T1[16];  // T_base_sensor as Matrix4f, column-major
   float T2[16];  // T_world_base as Matrix4f, column-major
@@ -272,7 +283,8 @@ struct ScatterParams {
   float* obstacle;
   const uint32_t* touched_keys;
   size_t obstacle_cells;
-  uint32_t index_base;  // point index of element 0 (multi-GPU: the slice's offset in the scan)
+  uint32_t index_base;  // point index of element 0
+  const ShardSlice* slice;  // multi-GPU: the slice K1 binned (overrides n / index_base, offsets intensity)
 };
 
 // back prologue of a scan in a batch: the map writes the commit / scatter kernels do in the
@@ -364,8 +376,9 @@ int tile_estimate_debug_cta_ns(unsigned long long* out1024);  // entry/exit ns o
 #endif
 int tile_estimate_configure();  // one-time cudaFuncSetAttribute (dynamic smem); returns cudaError_t
 // multi-GPU GLOBAL map (kernels_tile.cu)
-void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, uint32_t* zero_a, uint32_t* zero_b,
-                        size_t n_words, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
+                        ShardSlice* slice_out, uint32_t* zero_a, uint32_t* zero_b, size_t n_words,
+                        uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
                                 LaunchCounter& lc);

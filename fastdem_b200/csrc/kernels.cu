@@ -141,10 +141,18 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   pdl_launch_dependents();  // K2 may start launching; it waits for this grid at its pdl_wait()
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  // multi-GPU front half: the slice was decided on the device (shard_begin_kernel); the grid
+  // covers the whole scan and the CTAs beyond the slice leave at once
+  uint32_t n_pts = p.n, in_base = 0;
+  if (p.slice) {
+    n_pts = p.slice->count;
+    in_base = p.slice->begin;
+    if (blockIdx.x * blockDim.x >= n_pts) return;
+  }
   // the point load does not depend on the geometry: put it in flight first
   float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   bool finite = true;
-  if (i < p.n) {
+  if (i < n_pts) {
     if (p.raw) {
       // nanopcl::from(msg): x/y/z floats at their field offsets, w = 1; non-finite points are
       // skipped before anything else sees them (bridge/ros/impl.hpp:237-244)
@@ -197,7 +205,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
       }
       }
     } else {
-      q = __ldg(&p.xyzw[i]);
+      q = __ldg(&p.xyzw[in_base + i]);
     }
   }
   if (threadIdx.x == 0) {
@@ -214,14 +222,14 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
 
   bool kept = false, inside = false;
   uint32_t key = p.invalid_key;
-  if (i < p.n) {
+  if (i < n_pts) {
     float var_z = 0.0f;
     if (p.input_frame == INPUT_SENSOR_FRAME) {
       // preprocessScan (fastdem/src/fastdem.cpp:164-190)
       float S[9];
       if (p.cov9) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) S[k] = __ldg(&p.cov9[static_cast<size_t>(i) * 9 + k]);
+        for (int k = 0; k < 9; ++k) S[k] = __ldg(&p.cov9[static_cast<size_t>(in_base + i) * 9 + k]);
       } else {
         sensor_covariance(p, q, S);
       }
@@ -267,7 +275,7 @@ preprocess_bin_kernel(const __grid_constant__ PreprocessParams p,
   }
 
   if (p.raw) {
-    const uint32_t fin_m = __ballot_sync(0xffffffffu, finite && i < p.n);
+    const uint32_t fin_m = __ballot_sync(0xffffffffu, finite && i < n_pts);
     if (lane == 0 && fin_m) atomicAdd(&counters[CNT_FINITE], __popc(fin_m));
   }
   const uint32_t kept_m = __ballot_sync(0xffffffffu, kept);

@@ -94,12 +94,18 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   // all loads of this thread are independent: issue them together
   const uint32_t n_inside = p.counters[CNT_INSIDE];
   const uint32_t n_prev = p.st_cur->touched_count;
-  if (i < p.n) {
+  uint32_t n_pts = p.n, index_base = p.index_base;
+  if (p.slice) {   // multi-GPU front half: the slice K1 binned (no obstacle work on this path)
+    n_pts = p.slice->count;
+    index_base = p.slice->begin;
+    if (blockIdx.x * blockDim.x >= n_pts) return;
+  }
+  if (i < n_pts) {
     key = __ldg(&p.keys[i]);
     const float4 q = __ldg(&p.pm[i]);
     const bool has_i = p.intensity != nullptr;
-    const float in = has_i ? __ldg(&p.intensity[i]) : 0.0f;
-    if (key != INV) v = obs_from_point(q.z, q.w, in, has_i, i + p.index_base);
+    const float in = has_i ? __ldg(&p.intensity[p.slice ? index_base + i : i]) : 0.0f;
+    if (key != INV) v = obs_from_point(q.z, q.w, in, has_i, i + index_base);
   }
   // updateObstacle's map_.clear(obstacle) (elevation_mapping.cpp:146) restricted to the cells
   // that can hold a value: those the last observing scan touched (the whole layer when the
@@ -550,8 +556,11 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
         pub.host_out[CNT_COUNT + lane] = w;
         reinterpret_cast<uint32_t*>(pub.st_cur)[lane] = w;
       }
+      const uint32_t cells = __shfl_sync(0xffffffffu, c, CNT_CELLS);
       if (SHARD && lane < shp->world) {
-        // every record of this scan has been read: the sources may reuse the buffers
+        // every record of this scan has been read: the sources may reuse the buffers; with the
+        // flag goes this stripe's load, which the slice split of scan seq + 2 is derived from
+        shp->peer_hdr[lane]->load[shp->seq & 1u][shp->rank] = cells;
         __threadfence_system();
         st_release_sys(&shp->peer_hdr[lane]->consumed[shp->rank], shp->seq);
       }
@@ -782,12 +791,60 @@ tile_estimate_shard_kernel(const __grid_constant__ EstimateParams p,
 // buffers this scan is about to overwrite (scan seq - 2 used the same parity), then re-arm the
 // bucket tables and the scan counters.
 __global__ void __launch_bounds__(256)
-shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, uint32_t* __restrict__ zero_a,
+shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
+                   ShardSlice* __restrict__ slice_out, uint32_t* __restrict__ zero_a,
                    uint32_t* __restrict__ zero_b, size_t n_words, uint32_t* __restrict__ counters) {
   if (threadIdx.x < world && seq > 2) {
     while (ld_acquire_sys(&hdr->consumed[threadIdx.x]) + 2u < seq) __nanosleep(64);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // ── this rank's slice of the scan ──
+    // Every owner published, with consumed[d] = seq - 2, how many cells of its stripe that scan
+    // touched: the same numbers on every rank, so every rank derives the same split, in integer
+    // arithmetic.  A rank's work is (its share of the points) + (its share of the cells), both
+    // as fractions in 1/65536; the shares of the points level that sum (water-filling): a rank
+    // that owns most of the cells bins few points or none, the ranks with idle stripes bin the
+    // rest.  Before any load is known (first two scans, or no cells at all): equal slices.
+    uint32_t q[kMaxShards], share[kMaxShards];
+    uint64_t total = 0;
+    for (int d = 0; d < world; ++d) {
+      q[d] = seq > 2 ? ld_relaxed_sys(&hdr->load[seq & 1u][d]) : 0u;
+      total += q[d];
+    }
+    constexpr uint32_t ONE = 65536u;
+    if (total == 0) {
+      for (int d = 0; d < world; ++d) share[d] = ONE / static_cast<uint32_t>(world);
+    } else {
+      for (int d = 0; d < world; ++d) q[d] = static_cast<uint32_t>(static_cast<uint64_t>(q[d]) * ONE / total);
+      uint32_t active = (1u << world) - 1u, level = 0;
+      for (int it = 0; it < world; ++it) {
+        uint32_t sum = ONE, cnt = 0;
+        for (int d = 0; d < world; ++d)
+          if (active >> d & 1u) { sum += q[d]; ++cnt; }
+        level = sum / cnt;
+        uint32_t drop = 0;
+        for (int d = 0; d < world; ++d)
+          if ((active >> d & 1u) && q[d] > level) drop |= 1u << d;
+        if (!drop) break;
+        active &= ~drop;   // (the rank with the smallest load always stays)
+      }
+      for (int d = 0; d < world; ++d) share[d] = (active >> d & 1u) ? level - q[d] : 0u;
+    }
+    // boundaries: cumulative shares scaled to the scan, warp-aligned; the last rank with a
+    // share takes the rounding remainder
+    uint32_t acc = 0, total_share = 0;
+    for (int d = 0; d < world; ++d) total_share += share[d];
+    uint32_t b0 = 0, b1 = 0;
+    for (int d = 0; d <= rank; ++d) {
+      b0 = b1;
+      acc += share[d];
+      b1 = acc == total_share ? n_scan
+                              : static_cast<uint32_t>(static_cast<uint64_t>(n_scan) * acc / total_share) & ~31u;
+    }
+    slice_out->begin = b0;
+    slice_out->count = b1 - b0;
+  }
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words; i += stride) {
     zero_a[i] = 0u;
@@ -873,24 +930,30 @@ shard_gather_kernel(const __grid_constant__ ShardBackArgs a, uint32_t* __restric
       }
     }
   }
-  // job list: one thread per bucket of the stripe, `world` remote 4-byte reads each (the counts
-  // were final before the ready flag was released)
+  // job list: one thread per bucket of the stripe; the sources' counts and first slots (final
+  // before the ready flag was released) are `2 * world` independent remote 4-byte reads, all in
+  // flight together; one list-slot atomic per warp
   const uint32_t g0 = static_cast<uint32_t>(a.rank) * a.bps;
-  for (size_t b = tid; b < a.bps; b += nthreads) {
+  const int lane = threadIdx.x & 31;
+  for (size_t b0 = tid - lane; b0 < a.bps; b0 += nthreads) {
+    const size_t b = b0 + lane;
     ShardJob J;
     J.bucket = static_cast<uint32_t>(b);
     J.total = 0;
 #pragma unroll
     for (int s = 0; s < kMaxShards; ++s) {
-      J.cnt[s] = s < a.world ? ld_relaxed_sys(&a.peer_cursor[s][g0 + b]) : 0u;
-      J.off[s] = 0;
-      J.total += J.cnt[s];
+      const bool on = s < a.world && b < a.bps;
+      J.cnt[s] = on ? ld_relaxed_sys(&a.peer_cursor[s][g0 + b]) : 0u;
+      J.off[s] = on ? ld_relaxed_sys(&a.peer_offset[s][g0 + b]) : 0u;
     }
-    if (J.total == 0) continue;
 #pragma unroll
-    for (int s = 0; s < kMaxShards; ++s)
-      if (J.cnt[s]) J.off[s] = ld_relaxed_sys(&a.peer_offset[s][g0 + b]);
-    a.jobs[atomicAdd(&counters[CNT_BUCKETS], 1u)] = J;
+    for (int s = 0; s < kMaxShards; ++s) J.total += J.cnt[s];
+    const uint32_t live = __ballot_sync(0xffffffffu, J.total != 0u);
+    if (!live) continue;
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(&counters[CNT_BUCKETS], static_cast<uint32_t>(__popc(live)));
+    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(live & ((1u << lane) - 1u));
+    if (J.total) a.jobs[slot] = J;
   }
 }
 
@@ -940,9 +1003,10 @@ void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounte
   ++lc.mine;
 }
 
-void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, uint32_t* zero_a, uint32_t* zero_b,
-                        size_t n_words, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
-  shard_begin_kernel<<<148, 256, 0, s>>>(hdr, seq, world, zero_a, zero_b, n_words, counters);
+void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
+                        ShardSlice* slice_out, uint32_t* zero_a, uint32_t* zero_b, size_t n_words,
+                        uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
+  shard_begin_kernel<<<148, 256, 0, s>>>(hdr, seq, world, rank, n_scan, slice_out, zero_a, zero_b, n_words, counters);
   ++lc.mine;
 }
 void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
