@@ -685,9 +685,10 @@ def measure_sharded(cx: Ctx, wl, sampler):
         has_i, has_c = host[0]["intensity"] is not None, host[0]["rgb"] is not None
         scan_bytes = n * (16 + (4 if has_i else 0) + (3 if has_c else 0))
         n_dev = ring_size(scan_bytes)
-        # the scans live ONCE, in the ingest rank's HBM; every rank maps them (CUDA IPC) and its K1
-        # reads its slice across NVLink while binning it
-        ring = PeerScanRing(n_dev, n, has_i, has_c, device=dev.index, src=0)
+        # every rank holds the scans in its own HBM (a deployment uploads the scan to every GPU over
+        # that GPU's own PCIe link, in parallel): which slice a rank bins is decided on the device
+        # from the stripes' loads, so any rank may be handed most of a scan
+        ring = PeerScanRing(n_dev, n, has_i, has_c, device=dev.index, src=0, replicated=True)
         for j in range(n_dev):
             s = host[j % n_host]
             ring.fill(j, s["xyzw"], s["intensity"], s["rgb"])
@@ -748,10 +749,10 @@ def measure_sharded(cx: Ctx, wl, sampler):
             dist.all_reduce(t)
             stats.append(type("S", (), {"n_kept": float(t[0]), "n_cells": float(t[1]), "n_voxels": 0})())
 
-        # ── e2e: host scan on the ingest rank -> a ring slot in its HBM (pinned H2D) -> every rank
-        #    integrates straight out of that slot -> per-rank stats read back ──
+        # ── e2e: every rank uploads the host scan (pinned) into a slot of its own ring over its own
+        #    PCIe link -> integrates out of that slot -> per-rank stats read back ──
         pin = None
-        if rank == 0:
+        if True:
             pin = [dict(xyzw=torch.from_numpy(s["xyzw"]).pin_memory(),
                         intensity=None if not has_i else torch.from_numpy(s["intensity"]).pin_memory(),
                         rgb=None if not has_c else torch.from_numpy(s["rgb"]).pin_memory()) for s in host]
@@ -759,11 +760,9 @@ def measure_sharded(cx: Ctx, wl, sampler):
         def e2e_steps(count):
             for _ in range(count):
                 kk = K[0]
-                if rank == 0:
-                    p = pin[kk % n_host]
-                    ring.fill(kk % n_dev, p["xyzw"], p["intensity"], p["rgb"])
-                    torch.cuda.synchronize(dev)
-                dist.barrier()      # the slot is complete before any rank's K1 reads it
+                p = pin[kk % n_host]
+                ring.fill(kk % n_dev, p["xyzw"], p["intensity"], p["rgb"])
+                stream.synchronize()   # the slot is complete before this rank's front half reads it
                 sm.integrate(clouds[kk % n_dev], *pose_of(kk))
                 K[0] += 1
 
@@ -783,14 +782,17 @@ def measure_sharded(cx: Ctx, wl, sampler):
                            % args.min_region_s},
         "cpu_enqueue_us_per_step": cpu_enqueue_us, "gpu_launches": int(round(launches)), "library_launches": 0,
         "e2e": {"value": e2e_value, "unit": "scans/s", "mpoints_per_s": e2e_value * n / 1e6,
-                "ms_per_step": e_med / steps, "h2d_bytes_per_step": scan_bytes, "d2h_bytes_per_step": (32 + 88) * world,
+                "ms_per_step": e_med / steps, "h2d_bytes_per_step": scan_bytes * world,
+                "h2d_bytes_per_step_per_gpu": scan_bytes, "d2h_bytes_per_step": (32 + 88) * world,
                 "regions": len(e_all),
-                "how": "ingest rank: pinned host scan -> ring slot in its HBM; barrier; every rank integrates its "
-                       "slice out of that slot and reads its stats back; wall clock, median region"},
+                "how": "every rank: pinned host scan -> slot of its own ring over its own PCIe link (in parallel), "
+                       "then integrates the slice the device hands it and reads its stats back; wall clock, "
+                       "median region, max over ranks"},
         "roofline": {
             "bound": "hbm", "kernel": "whole scan",
-            "kernel_names": "per rank: shard_begin + preprocess_bin (slice) + shard_alloc + scatter_records + "
-                            "shard_publish_front | shard_gather + tile_estimate_shard (its stripe)",
+            "kernel_names": "per rank: shard_begin + preprocess_bin (slice) + shard_alloc + scatter_records (push) + "
+                            "shard_publish_front | shard_gather + tile_estimate_light_shard + tile_estimate_shard "
+                            "(its stripe)",
             "achieved": total_bytes / (step_ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
             "frac": total_bytes / (step_ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": total_bytes, "kernel_ms": step_ms,
@@ -801,11 +803,12 @@ def measure_sharded(cx: Ctx, wl, sampler):
             "workload": wl.name, "description": wl.description, "points_per_scan": n,
             "arithmetic": "float32 cell state and point math, float64 grid geometry (as the reference)",
             "map_cells": int(round(wl.map_width / wl.resolution)) * int(round(wl.map_height / wl.resolution)),
-            "parallelism": f"row-stripes x{world}: every rank bins 1/{world} of the scan (read in place from the "
-                           f"ingest GPU over NVLink, CUDA IPC), owners pull their buckets' records from all ranks "
-                           f"(TMA reads of peer memory), device-side ready/consumed flags; no collective on the data path",
-            "l2": f"inputs larger than L2: {n_dev} distinct scan buffers = {n_dev * scan_bytes >> 20} MiB in the "
-                  "ingest rank's HBM, cycled",
+            "parallelism": f"row-stripes x{world}: every rank bins a slice of the scan sized on the device from "
+                           f"the stripes' loads (busy owners bin less), pushes each record into its owner's arena "
+                           f"(NVLink stores, CUDA IPC), owners estimate out of local memory; device-side "
+                           f"ready/consumed flags; no collective on the data path",
+            "l2": f"inputs larger than L2: {n_dev} distinct scan buffers = {n_dev * scan_bytes >> 20} MiB in "
+                  "every rank's HBM, cycled",
             "scan_ring": n_dev, "submission": "one fdem_shard_integrate per scan per rank"},
         "_timed_wall": (t_first, t_last),
     }

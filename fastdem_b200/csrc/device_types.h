@@ -285,6 +285,11 @@ struct ScatterParams {
   size_t obstacle_cells;
   uint32_t index_base;  // point index of element 0
   const ShardSlice* slice;  // multi-GPU: the slice K1 binned (overrides n / index_base, offsets intensity)
+  // multi-GPU: records are PUSHED — a record of a bucket of stripe d goes straight into this
+  // source's area of owner d's arena (peer-mapped; NVLink stores), so the owners' back halves
+  // read local memory only.  owner_bps = buckets per stripe, 0 on a single GPU (tb.records).
+  CellRecord* owner_records[kMaxShards];
+  uint32_t owner_bps;
 };
 
 // back prologue of a scan in a batch: the map writes the commit / scatter kernels do in the
@@ -359,7 +364,7 @@ KernelDesc desc_publish();
 KernelDesc desc_scatter_records(uint32_t n);
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits);
 KernelDesc desc_shard_begin();
-KernelDesc desc_shard_alloc();
+KernelDesc desc_shard_alloc(int world);
 KernelDesc desc_shard_publish_front();
 KernelDesc desc_shard_gather();
 KernelDesc desc_tile_estimate_shard(uint32_t bps);
@@ -379,7 +384,12 @@ int tile_estimate_configure();  // one-time cudaFuncSetAttribute (dynamic smem);
 void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
                         ShardSlice* slice_out, uint32_t* zero_a, uint32_t* zero_b, size_t n_words,
                         uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
-void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
+// counters: the front counter block; words [kShardSlotBase, kShardSlotBase + world) are the record
+// slots handed out so far in every owner's area
+constexpr int kShardSlotBase = 16;
+constexpr int kFrontCounterWords = 32;
+void launch_shard_alloc(const TileBuffers& tb, uint32_t bps, int world, uint32_t* counters, cudaStream_t s,
+                        LaunchCounter& lc);
 void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
                                 LaunchCounter& lc);
 void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);

@@ -145,7 +145,8 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
     if (lane == leader) base = atomicAdd(&p.tb.bucket_cursor[bucket], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = p.tb.bucket_offset[bucket] + base + __popc(peers & ((1u << lane) - 1u));
-    uint4* dst = reinterpret_cast<uint4*>(p.tb.records + slot);
+    CellRecord* area = p.owner_bps ? p.owner_records[bucket / p.owner_bps] : p.tb.records;
+    uint4* dst = reinterpret_cast<uint4*>(area + slot);
     dst[0] = make_uint4(key & ((1u << p.tb.bucket_bits) - 1u), __float_as_uint(v.mz),
                         __float_as_uint(v.mv), v.mi);
     dst[1] = make_uint4(__float_as_uint(v.xz), __float_as_uint(v.it), v.fi, v.li);
@@ -850,18 +851,22 @@ shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int r
     zero_a[i] = 0u;
     zero_b[i] = 0u;
   }
-  if (blockIdx.x == 0 && threadIdx.x < CNT_COUNT) counters[threadIdx.x] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x < kFrontCounterWords) counters[threadIdx.x] = 0u;
 }
 
 // FRONT: bucket segment allocation for every (stripe, bucket) of this rank's slice — the same
 // two-atomics-per-warp scheme as commit_move_clear_kernel's group A
 __global__ void __launch_bounds__(256)
-shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t* __restrict__ counters) {
+shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t bps, uint32_t* __restrict__ counters) {
+  // blockIdx.y = the owner whose buckets this CTA row places: slots are handed out per owner,
+  // because a bucket's records go into this source's area of ITS owner's arena
   const int lane = threadIdx.x & 31;
+  const uint32_t owner = blockIdx.y;
+  const size_t g0 = static_cast<size_t>(owner) * bps;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t b = tid; b - lane < tb.n_buckets; b += nthreads) {
-    const uint32_t cnt = b < tb.n_buckets ? tb.bucket_count[b] : 0u;
+  for (size_t b = tid; b - lane < bps; b += nthreads) {
+    const uint32_t cnt = b < bps ? tb.bucket_count[g0 + b] : 0u;
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -870,9 +875,9 @@ shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t* __restrict_
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t slot0 = 0;
-    if (lane == 0 && total) slot0 = atomicAdd(&counters[CNT_REC_SLOTS], total);
+    if (lane == 0 && total) slot0 = atomicAdd(&counters[kShardSlotBase + owner], total);
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-    if (cnt) tb.bucket_offset[b] = slot0 + incl - cnt;
+    if (cnt) tb.bucket_offset[g0 + b] = slot0 + incl - cnt;
   }
 }
 
@@ -1009,8 +1014,9 @@ void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uin
   shard_begin_kernel<<<148, 256, 0, s>>>(hdr, seq, world, rank, n_scan, slice_out, zero_a, zero_b, n_words, counters);
   ++lc.mine;
 }
-void launch_shard_alloc(const TileBuffers& tb, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
-  shard_alloc_kernel<<<148, 256, 0, s>>>(tb, counters);
+void launch_shard_alloc(const TileBuffers& tb, uint32_t bps, int world, uint32_t* counters, cudaStream_t s,
+                        LaunchCounter& lc) {
+  shard_alloc_kernel<<<dim3(148 / world + 1, world), 256, 0, s>>>(tb, bps, counters);
   ++lc.mine;
 }
 void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
@@ -1068,8 +1074,8 @@ KernelDesc desc_scatter_records(uint32_t n) {
 KernelDesc desc_shard_begin() {
   return KernelDesc{reinterpret_cast<const void*>(&shard_begin_kernel), dim3(148), dim3(256), 0};
 }
-KernelDesc desc_shard_alloc() {
-  return KernelDesc{reinterpret_cast<const void*>(&shard_alloc_kernel), dim3(148), dim3(256), 0};
+KernelDesc desc_shard_alloc(int world) {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_alloc_kernel), dim3(148 / world + 1, world), dim3(256), 0};
 }
 KernelDesc desc_shard_publish_front() {
   return KernelDesc{reinterpret_cast<const void*>(&shard_publish_front_kernel), dim3(1), dim3(32), 0};

@@ -365,10 +365,15 @@ class PeerScanRing:
     layout: xyzw (n x 16 B) | intensity (n x 4 B) | rgb (n x 3 B), each 256-byte aligned.
 
     Ordering is the caller's: a slot must not be rewritten while a rank may still read it (the
-    bench fills the ring once; the host->device e2e path brackets every step with a barrier)."""
+    bench fills the ring once; the host->device e2e path brackets every step with a barrier).
+
+    replicated=True: every rank keeps its OWN copy of the ring in its own HBM and fills it itself
+    (every rank uploads the scan over its own PCIe link, in parallel) — no IPC, no peer reads:
+    what ShardedMapper wants when the slice a rank bins is decided on the device (any rank may
+    be handed most of a scan, and reading it across NVLink would bound its K1)."""
 
     def __init__(self, n_slots: int, max_points: int, has_intensity: bool, has_color: bool, *,
-                 device: int, src: int = 0, group=None):
+                 device: int, src: int = 0, group=None, replicated: bool = False):
         import ctypes as C
         import torch.distributed as dist
         from . import api, capi
@@ -384,7 +389,8 @@ class PeerScanRing:
         self.off_c = self.off_i + (al(max_points * 4) if has_intensity else 0)
         self.slot_bytes = self.off_c + (al(max_points * 3) if has_color else 0)
         self.base = []          # device address of every slot in THIS process
-        self._owned = self.rank == src
+        self.replicated = replicated
+        self._owned = replicated or self.rank == src
         handles = []
         if self._owned:
             for _ in range(n_slots):
@@ -394,7 +400,7 @@ class PeerScanRing:
                 h = capi.FdemIpcHandle()
                 capi.check(self.lib.fdem_ipc_export(device, p, self.slot_bytes, C.byref(h)))
                 handles.append(bytes(h))
-        if self.world > 1:
+        if self.world > 1 and not replicated:
             box = [handles]
             dist.broadcast_object_list(box, src=src, group=group)
             handles = box[0]
@@ -416,7 +422,8 @@ class PeerScanRing:
         return pc
 
     def fill(self, slot: int, xyzw, intensity=None, rgb=None, stream=None):
-        """Ingest rank only: copy one scan (numpy / pinned torch / CUDA torch) into a slot."""
+        """Ingest rank only (every rank of a replicated ring): copy one scan (numpy / pinned torch /
+        CUDA torch) into a slot."""
         if not self._owned:
             return
         import torch

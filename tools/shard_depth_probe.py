@@ -20,7 +20,7 @@ def main():
     cfg = wl.config()
     cfg.mode = capi.MODE_GLOBAL
     n = wl.points_per_scan
-    ring = sharded.PeerScanRing(4, n, wl.has_intensity, wl.has_color, device=rank, src=0)
+    ring = sharded.PeerScanRing(4, n, wl.has_intensity, wl.has_color, device=rank, src=0, replicated=True)
     scans = [syn.make_scan(wl, k) for k in range(4)]
     for j, s in enumerate(scans):
         ring.fill(j, s["xyzw"], s["intensity"], s["rgb"])
