@@ -81,11 +81,23 @@ __device__ __forceinline__ CellObs obs_of(const CellRecord& r) {
   return o;
 }
 
+// system-scope flag traffic of the multi-GPU handshake (flags live in peer-mapped memory)
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ───────────────────────────── L1: scatter into bucket segments ──────────────
-__global__ void __launch_bounds__(kThreads)
-scatter_records_kernel(const __grid_constant__ ScatterParams p) {
-  pdl_launch_dependents();
-  pdl_wait();  // K1 (keys, pm) and K2 (bucket segments) are complete from here on
+__device__ __forceinline__ void scatter_records_body(const ScatterParams& p, uint32_t n_pts, uint32_t index_base) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const uint32_t INV = p.invalid_key;
@@ -94,12 +106,6 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   // all loads of this thread are independent: issue them together
   const uint32_t n_inside = p.counters[CNT_INSIDE];
   const uint32_t n_prev = p.st_cur->touched_count;
-  uint32_t n_pts = p.n, index_base = p.index_base;
-  if (p.slice) {   // multi-GPU front half: the slice K1 binned (no obstacle work on this path)
-    n_pts = p.slice->count;
-    index_base = p.slice->begin;
-    if (blockIdx.x * blockDim.x >= n_pts) return;
-  }
   if (i < n_pts) {
     key = __ldg(&p.keys[i]);
     const float4 q = __ldg(&p.pm[i]);
@@ -150,6 +156,37 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
     dst[0] = make_uint4(key & ((1u << p.tb.bucket_bits) - 1u), __float_as_uint(v.mz),
                         __float_as_uint(v.mv), v.mi);
     dst[1] = make_uint4(__float_as_uint(v.xz), __float_as_uint(v.it), v.fi, v.li);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+scatter_records_kernel(const __grid_constant__ ScatterParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // K1 (keys, pm) and K2 (bucket segments) are complete from here on
+  if (!p.slice) {
+    scatter_records_body(p, p.n, p.index_base);
+    return;
+  }
+  // ── multi-GPU front half: the slice K1 binned (decided on the device); the grid covers the
+  //    whole scan and the CTAs beyond the slice have nothing to scatter ──
+  const uint32_t n_pts = p.slice->count;
+  if (blockIdx.x * blockDim.x < n_pts) scatter_records_body(p, n_pts, p.slice->begin);
+  // the LAST CTA to finish publishes the front half.  The CTA's record stores (peer memory) are
+  // ordered before its ticket by the barrier + ONE system-scope fence (fences are cumulative).
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < static_cast<unsigned>(p.front.world)) {
+    __threadfence();
+    const int d = threadIdx.x;
+    const uint32_t inside = *reinterpret_cast<const volatile uint32_t*>(&p.counters[CNT_INSIDE]);
+    p.front.peer_hdr[d]->inside[p.front.seq & 1u][p.front.rank] = inside;
+    __threadfence_system();
+    st_release_sys(&p.front.peer_hdr[d]->ready[p.front.rank], p.front.seq);
   }
 }
 
@@ -225,21 +262,6 @@ template <typename S_>
 __device__ __forceinline__ void acc_store(S_& S, uint32_t a, const CellObs& t) {
   S.a_mz[a] = t.mz; S.a_mv[a] = t.mv; S.a_mi[a] = t.mi; S.a_xz[a] = t.xz;
   S.a_it[a] = t.it; S.a_fi[a] = t.fi; S.a_li[a] = t.li;
-}
-
-// system-scope flag traffic of the multi-GPU handshake (flags live in peer-mapped memory)
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 
 // stage records [cs, cs + cn) of a sharded bucket — the concatenation of its pieces in the
@@ -793,8 +815,10 @@ tile_estimate_shard_kernel(const __grid_constant__ EstimateParams p,
 // bucket tables and the scan counters.
 __global__ void __launch_bounds__(256)
 shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
-                   ShardSlice* __restrict__ slice_out, uint32_t* __restrict__ zero_a,
-                   uint32_t* __restrict__ zero_b, size_t n_words, uint32_t* __restrict__ counters) {
+                   uint32_t back_weight, ShardSlice* __restrict__ slice_out, uint32_t* __restrict__ counters) {
+  // one warp: wait until every owner is done with the buffers of scan seq - 2 (same parity),
+  // decide this rank's slice, re-arm the front counters (the tables are re-armed by
+  // shard_alloc_kernel, which visits every bucket anyway)
   if (threadIdx.x < world && seq > 2) {
     while (ld_acquire_sys(&hdr->consumed[threadIdx.x]) + 2u < seq) __nanosleep(64);
   }
@@ -803,10 +827,11 @@ shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int r
     // ── this rank's slice of the scan ──
     // Every owner published, with consumed[d] = seq - 2, how many cells of its stripe that scan
     // touched: the same numbers on every rank, so every rank derives the same split, in integer
-    // arithmetic.  A rank's work is (its share of the points) + (its share of the cells), both
-    // as fractions in 1/65536; the shares of the points level that sum (water-filling): a rank
-    // that owns most of the cells bins few points or none, the ranks with idle stripes bin the
-    // rest.  Before any load is known (first two scans, or no cells at all): equal slices.
+    // arithmetic.  A rank's work is (its share of the points) + w * (its share of the cells),
+    // both as fractions in 1/65536, w = back_weight / 256 = the cost of a whole back half in
+    // units of a whole front half; the shares of the points level that sum (water-filling): a
+    // rank that owns most of the cells bins few points or none, the ranks with idle stripes bin
+    // the rest.  Before any load is known (first two scans, or no cells at all): equal slices.
     uint32_t q[kMaxShards], share[kMaxShards];
     uint64_t total = 0;
     for (int d = 0; d < world; ++d) {
@@ -817,7 +842,8 @@ shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int r
     if (total == 0) {
       for (int d = 0; d < world; ++d) share[d] = ONE / static_cast<uint32_t>(world);
     } else {
-      for (int d = 0; d < world; ++d) q[d] = static_cast<uint32_t>(static_cast<uint64_t>(q[d]) * ONE / total);
+      for (int d = 0; d < world; ++d)
+        q[d] = static_cast<uint32_t>(static_cast<uint64_t>(q[d]) * ONE / total * back_weight >> 8);
       uint32_t active = (1u << world) - 1u, level = 0;
       for (int it = 0; it < world; ++it) {
         uint32_t sum = ONE, cnt = 0;
@@ -846,11 +872,6 @@ shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int r
     slice_out->begin = b0;
     slice_out->count = b1 - b0;
   }
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words; i += stride) {
-    zero_a[i] = 0u;
-    zero_b[i] = 0u;
-  }
   if (blockIdx.x == 0 && threadIdx.x < kFrontCounterWords) counters[threadIdx.x] = 0u;
 }
 
@@ -867,6 +888,12 @@ shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t bps, uint32_
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t b = tid; b - lane < bps; b += nthreads) {
     const uint32_t cnt = b < bps ? tb.bucket_count[g0 + b] : 0u;
+    if (b < bps) {
+      // re-arm: the histogram for this rank's next scan, the record cursors (peer-visible;
+      // the owners finished reading this parity's — shard_begin_kernel waited for that)
+      if (cnt) tb.bucket_count[g0 + b] = 0u;
+      tb.bucket_cursor[g0 + b] = 0u;
+    }
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -879,18 +906,6 @@ shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t bps, uint32_
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (cnt) tb.bucket_offset[g0 + b] = slot0 + incl - cnt;
   }
-}
-
-// FRONT, last kernel: tell every owner that this rank's records of scan `seq` are in place
-// (kernel boundaries have made them visible device-wide; the flag is a system-scope release)
-__global__ void shard_publish_front_kernel(const __grid_constant__ ShardFrontArgs a,
-                                           const uint32_t* __restrict__ counters) {
-  const int d = threadIdx.x;
-  if (d >= a.world) return;
-  const uint32_t inside = counters[CNT_INSIDE];
-  a.peer_hdr[d]->inside[a.seq & 1u][a.rank] = inside;
-  __threadfence_system();
-  st_release_sys(&a.peer_hdr[d]->ready[a.rank], a.seq);
 }
 
 // BACK, first kernel on every rank: wait for every source's front half, then (a) list the
@@ -1009,19 +1024,14 @@ void launch_scatter_records(const ScatterParams& p, cudaStream_t s, LaunchCounte
 }
 
 void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
-                        ShardSlice* slice_out, uint32_t* zero_a, uint32_t* zero_b, size_t n_words,
-                        uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
-  shard_begin_kernel<<<148, 256, 0, s>>>(hdr, seq, world, rank, n_scan, slice_out, zero_a, zero_b, n_words, counters);
+                        uint32_t back_weight, ShardSlice* slice_out, uint32_t* counters, cudaStream_t s,
+                        LaunchCounter& lc) {
+  shard_begin_kernel<<<1, 32, 0, s>>>(hdr, seq, world, rank, n_scan, back_weight, slice_out, counters);
   ++lc.mine;
 }
 void launch_shard_alloc(const TileBuffers& tb, uint32_t bps, int world, uint32_t* counters, cudaStream_t s,
                         LaunchCounter& lc) {
   shard_alloc_kernel<<<dim3(148 / world + 1, world), 256, 0, s>>>(tb, bps, counters);
-  ++lc.mine;
-}
-void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
-                                LaunchCounter& lc) {
-  shard_publish_front_kernel<<<1, 32, 0, s>>>(a, counters);
   ++lc.mine;
 }
 void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc) {
@@ -1072,13 +1082,10 @@ KernelDesc desc_scatter_records(uint32_t n) {
                     dim3((n + kThreads - 1) / kThreads), dim3(kThreads), 0};
 }
 KernelDesc desc_shard_begin() {
-  return KernelDesc{reinterpret_cast<const void*>(&shard_begin_kernel), dim3(148), dim3(256), 0};
+  return KernelDesc{reinterpret_cast<const void*>(&shard_begin_kernel), dim3(1), dim3(32), 0};
 }
 KernelDesc desc_shard_alloc(int world) {
   return KernelDesc{reinterpret_cast<const void*>(&shard_alloc_kernel), dim3(148 / world + 1, world), dim3(256), 0};
-}
-KernelDesc desc_shard_publish_front() {
-  return KernelDesc{reinterpret_cast<const void*>(&shard_publish_front_kernel), dim3(1), dim3(32), 0};
 }
 KernelDesc desc_shard_gather() {
   return KernelDesc{reinterpret_cast<const void*>(&shard_gather_kernel), dim3(148), dim3(256), 0};
