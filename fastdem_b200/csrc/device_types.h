@@ -290,10 +290,6 @@ struct ScatterParams {
   // read local memory only.  owner_bps = buckets per stripe, 0 on a single GPU (tb.records).
   CellRecord* owner_records[kMaxShards];
   uint32_t owner_bps;
-  // ... and the LAST CTA of the grid to finish publishes the front half to the owners (inside
-  // count + ready flag): no separate publish kernel
-  ShardFrontArgs front;
-  uint32_t* ticket;
 };
 
 // back prologue of a scan in a batch: the map writes the commit / scatter kernels do in the
@@ -369,6 +365,7 @@ KernelDesc desc_scatter_records(uint32_t n);
 KernelDesc desc_tile_estimate(uint32_t n_buckets, uint32_t bucket_bits);
 KernelDesc desc_shard_begin();
 KernelDesc desc_shard_alloc(int world);
+KernelDesc desc_shard_publish_front();
 KernelDesc desc_shard_gather();
 KernelDesc desc_tile_estimate_shard(uint32_t bps);
 KernelDesc desc_tile_estimate_light();
@@ -393,6 +390,8 @@ constexpr int kShardSlotBase = 16;
 constexpr int kFrontCounterWords = 32;
 void launch_shard_alloc(const TileBuffers& tb, uint32_t bps, int world, uint32_t* counters, cudaStream_t s,
                         LaunchCounter& lc);
+void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
+                                LaunchCounter& lc);
 void launch_shard_gather(const ShardBackArgs& a, uint32_t* counters, cudaStream_t s, LaunchCounter& lc);
 // light pass of K3t: one warp per bucket with <= 128 records; bigger buckets go to the heavy list
 void launch_tile_estimate_light(const EstimateParams& p, const TileBuffers& tb, uint32_t* counters,

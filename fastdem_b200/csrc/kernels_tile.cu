@@ -171,23 +171,6 @@ scatter_records_kernel(const __grid_constant__ ScatterParams p) {
   //    whole scan and the CTAs beyond the slice have nothing to scatter ──
   const uint32_t n_pts = p.slice->count;
   if (blockIdx.x * blockDim.x < n_pts) scatter_records_body(p, n_pts, p.slice->begin);
-  // the LAST CTA to finish publishes the front half.  The CTA's record stores (peer memory) are
-  // ordered before its ticket by the barrier + ONE system-scope fence (fences are cumulative).
-  __shared__ uint32_t s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < static_cast<unsigned>(p.front.world)) {
-    __threadfence();
-    const int d = threadIdx.x;
-    const uint32_t inside = *reinterpret_cast<const volatile uint32_t*>(&p.counters[CNT_INSIDE]);
-    p.front.peer_hdr[d]->inside[p.front.seq & 1u][p.front.rank] = inside;
-    __threadfence_system();
-    st_release_sys(&p.front.peer_hdr[d]->ready[p.front.rank], p.front.seq);
-  }
 }
 
 // Tuning probes, compiled only with -DFDEM_PROBES (tools/phase_probe.py): phase timeline of
@@ -908,6 +891,20 @@ shard_alloc_kernel(const __grid_constant__ TileBuffers tb, uint32_t bps, uint32_
   }
 }
 
+// FRONT, last kernel: tell every owner that this rank's records of scan `seq` are in place (the
+// kernel boundary behind the scatter has completed its stores into the owners' arenas — cheaper
+// than a system-scope fence in each of its thousands of CTAs, which was measured: +14 us; the
+// flag is a system-scope release)
+__global__ void shard_publish_front_kernel(const __grid_constant__ ShardFrontArgs a,
+                                           const uint32_t* __restrict__ counters) {
+  const int d = threadIdx.x;
+  if (d >= a.world) return;
+  const uint32_t inside = counters[CNT_INSIDE];
+  a.peer_hdr[d]->inside[a.seq & 1u][a.rank] = inside;
+  __threadfence_system();
+  st_release_sys(&a.peer_hdr[d]->ready[a.rank], a.seq);
+}
+
 // BACK, first kernel on every rank: wait for every source's front half, then (a) list the
 // non-empty buckets of this rank's stripe with their record pieces, (b) do the map-side
 // bookkeeping the one-GPU pipeline does in K2 / scatter: the obstacle reset of the last observing
@@ -1029,6 +1026,11 @@ void launch_shard_begin(ShardHeader* hdr, uint32_t seq, int world, int rank, uin
   shard_begin_kernel<<<1, 32, 0, s>>>(hdr, seq, world, rank, n_scan, back_weight, slice_out, counters);
   ++lc.mine;
 }
+void launch_shard_publish_front(const ShardFrontArgs& a, const uint32_t* counters, cudaStream_t s,
+                                LaunchCounter& lc) {
+  shard_publish_front_kernel<<<1, 32, 0, s>>>(a, counters);
+  ++lc.mine;
+}
 void launch_shard_alloc(const TileBuffers& tb, uint32_t bps, int world, uint32_t* counters, cudaStream_t s,
                         LaunchCounter& lc) {
   shard_alloc_kernel<<<dim3(148 / world + 1, world), 256, 0, s>>>(tb, bps, counters);
@@ -1083,6 +1085,9 @@ KernelDesc desc_scatter_records(uint32_t n) {
 }
 KernelDesc desc_shard_begin() {
   return KernelDesc{reinterpret_cast<const void*>(&shard_begin_kernel), dim3(1), dim3(32), 0};
+}
+KernelDesc desc_shard_publish_front() {
+  return KernelDesc{reinterpret_cast<const void*>(&shard_publish_front_kernel), dim3(1), dim3(32), 0};
 }
 KernelDesc desc_shard_alloc(int world) {
   return KernelDesc{reinterpret_cast<const void*>(&shard_alloc_kernel), dim3(148 / world + 1, world), dim3(256), 0};

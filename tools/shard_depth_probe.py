@@ -46,18 +46,22 @@ def main():
 
     threading.Thread(target=watchdog, daemon=True).start()
     k = 0
+    from fastdem_b200 import api
+    clouds = [ring.cloud(j, n) for j in range(4)]
+    poses = [tuple(api._iso(t) for t in syn.pose(wl, kk)) for kk in range(512)]   # the host must not be the bound
     depths = [int(x) for x in os.environ.get("PROBE_DEPTHS", "1,2,3,4,8,20,40").split(",")]
     for depth in depths:
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(depth):
-            sm.integrate_async(ring.cloud(k % 4, n), *syn.pose(wl, k))
+            sm.integrate_async(clouds[k % 4], *poses[k % 512])
             k += 1
+        t_enq = time.perf_counter() - t0
         st = sm.wait()
         dt = time.perf_counter() - t0
-        if True:
-            print(f"rank {rank} depth {depth}: {1e6 * dt / depth:.1f} us/scan  (n_cells {st.n_cells})", flush=True)
+        print(f"rank {rank} depth {depth}: {1e6 * dt / depth:.1f} us/scan  (host enqueue {1e6 * t_enq / depth:.1f} us/scan, "
+              f"n_cells {st.n_cells})", flush=True)
     dist.barrier()
     sm.close()
     dist.destroy_process_group()
