@@ -113,17 +113,26 @@ FDEM_HD int32_t shard_of_row(const ShardGeom& sg, int32_t row, int32_t& row_begi
 
 // what a source rank publishes for the owners, and the flags of the two-way handshake; lives at
 // the start of every rank's exchange arena (peer-mapped by all other ranks)
+// scans in flight between a rank's front half and the owners' back halves: every per-scan buffer of
+// the exchange (tables, record areas, counters, flags' payload) exists kShardDepth times, indexed
+// by seq % kShardDepth; a source may run its front half up to kShardDepth scans ahead of the
+// slowest owner.  Measured on 2 x B200 (C5): depth 4 = 14.81 K scans/s, depth 2 = 14.76 K — the
+// job is bound by the busiest owner's serial back-half chain, not by the buffering depth; 2 is
+// the depth validated at N = 2, 4 and 8.
+constexpr uint32_t kShardDepth = 2;
+
 struct ShardHeader {
   uint32_t ready[kMaxShards];        // [s] written by source s: front half of scan #ready[s] is complete
   uint32_t consumed[kMaxShards];     // [d] written by owner d: it has finished reading scan #consumed[d]
-  uint32_t inside[2][kMaxShards];    // [scan parity][s]: points of source s's slice inside the map
-  uint32_t load[2][kMaxShards];      // [scan parity][d] written by owner d with consumed[d]: cells of its
-                                     // stripe that scan touched (what the slice split two scans later uses)
+  uint32_t inside[kShardDepth][kMaxShards];  // [seq % depth][s]: points of source s's slice inside the map
+  uint32_t load[kShardDepth][kMaxShards];    // [seq % depth][d] written by owner d with consumed[d]: cells of
+                                             // its stripe that scan touched (the slice split of scan
+                                             // seq + depth is derived from it)
   uint32_t _pad[16];
 };
 
 // A rank's slice of the scan for the front half, decided ON THE DEVICE by shard_begin_kernel from
-// the owners' loads of two scans ago (identical on every rank): ranks whose stripe got most of
+// the owners' loads of kShardDepth scans ago (identical on every rank): ranks whose stripe got most of
 // the cells — and so most of the back half — bin fewer points.
 struct ShardSlice {
   uint32_t begin, count;

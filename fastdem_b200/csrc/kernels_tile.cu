@@ -566,7 +566,7 @@ tile_estimate_body(const EstimateParams& p, const TileBuffers& tb, uint32_t* __r
       if (SHARD && lane < shp->world) {
         // every record of this scan has been read: the sources may reuse the buffers; with the
         // flag goes this stripe's load, which the slice split of scan seq + 2 is derived from
-        shp->peer_hdr[lane]->load[shp->seq & 1u][shp->rank] = cells;
+        shp->peer_hdr[lane]->load[shp->seq % kShardDepth][shp->rank] = cells;
         __threadfence_system();
         st_release_sys(&shp->peer_hdr[lane]->consumed[shp->rank], shp->seq);
       }
@@ -799,26 +799,26 @@ tile_estimate_shard_kernel(const __grid_constant__ EstimateParams p,
 __global__ void __launch_bounds__(256)
 shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int rank, uint32_t n_scan,
                    uint32_t back_weight, ShardSlice* __restrict__ slice_out, uint32_t* __restrict__ counters) {
-  // one warp: wait until every owner is done with the buffers of scan seq - 2 (same parity),
+  // one warp: wait until every owner is done with the buffers of scan seq - kShardDepth (same slot),
   // decide this rank's slice, re-arm the front counters (the tables are re-armed by
   // shard_alloc_kernel, which visits every bucket anyway)
-  if (threadIdx.x < world && seq > 2) {
-    while (ld_acquire_sys(&hdr->consumed[threadIdx.x]) + 2u < seq) __nanosleep(64);
+  if (threadIdx.x < world && seq > kShardDepth) {
+    while (ld_acquire_sys(&hdr->consumed[threadIdx.x]) + kShardDepth < seq) __nanosleep(64);
   }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     // ── this rank's slice of the scan ──
-    // Every owner published, with consumed[d] = seq - 2, how many cells of its stripe that scan
+    // Every owner published, with consumed[d] = seq - kShardDepth, how many cells of its stripe that scan
     // touched: the same numbers on every rank, so every rank derives the same split, in integer
     // arithmetic.  A rank's work is (its share of the points) + w * (its share of the cells),
     // both as fractions in 1/65536, w = back_weight / 256 = the cost of a whole back half in
     // units of a whole front half; the shares of the points level that sum (water-filling): a
     // rank that owns most of the cells bins few points or none, the ranks with idle stripes bin
-    // the rest.  Before any load is known (first two scans, or no cells at all): equal slices.
+    // the rest.  Before any load is known (first kShardDepth scans, or no cells at all): equal slices.
     uint32_t q[kMaxShards], share[kMaxShards];
     uint64_t total = 0;
     for (int d = 0; d < world; ++d) {
-      q[d] = seq > 2 ? ld_relaxed_sys(&hdr->load[seq & 1u][d]) : 0u;
+      q[d] = seq > kShardDepth ? ld_relaxed_sys(&hdr->load[seq % kShardDepth][d]) : 0u;
       total += q[d];
     }
     constexpr uint32_t ONE = 65536u;
@@ -900,7 +900,7 @@ __global__ void shard_publish_front_kernel(const __grid_constant__ ShardFrontArg
   const int d = threadIdx.x;
   if (d >= a.world) return;
   const uint32_t inside = counters[CNT_INSIDE];
-  a.peer_hdr[d]->inside[a.seq & 1u][a.rank] = inside;
+  a.peer_hdr[d]->inside[a.seq % kShardDepth][a.rank] = inside;
   __threadfence_system();
   st_release_sys(&a.peer_hdr[d]->ready[a.rank], a.seq);
 }
@@ -918,7 +918,7 @@ shard_gather_kernel(const __grid_constant__ ShardBackArgs a, uint32_t* __restric
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t t = 0;
-    for (int s = 0; s < a.world; ++s) t += ld_relaxed_sys(&a.hdr->inside[a.seq & 1u][s]);
+    for (int s = 0; s < a.world; ++s) t += ld_relaxed_sys(&a.hdr->inside[a.seq % kShardDepth][s]);
     s_inside = t;
   }
   __syncthreads();
