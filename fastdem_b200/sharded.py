@@ -278,11 +278,12 @@ class ShardedMapper:
     """fastdem::FastDEM on ONE GLOBAL map row-striped over the ranks — the path whose compute
     scales with the rank count (fdem_shard_* in the C-ABI, protocol in csrc/device_types.h):
 
-      front half, every rank: preprocessScan + binning of its 1/world slice of the scan, read in
-        place from wherever the scan lives (normally the ingest rank's HBM, over NVLink), for
-        EVERY stripe; the pre-reduced records stay in the rank's own arena;
-      back half, every rank: for the non-empty buckets of its own stripe, pull the record pieces
-        from all ranks' arenas (TMA bulk reads of peer memory) and run the per-cell estimator.
+      front half, every rank: preprocessScan + binning of its SLICE of the scan for EVERY stripe;
+        each pre-reduced record is stored straight into its owner's arena (NVLink stores).  The
+        slice is decided on the device from the stripes' loads two scans earlier: a rank whose
+        stripe owns most of the cells bins few points or none;
+      back half, every rank: the per-cell estimator over the records all sources pushed for the
+        non-empty buckets of its own stripe — local memory only.
 
     Device-side ready / consumed flags order the halves across ranks; torch.distributed is used
     ONCE, to exchange the CUDA IPC handles of the arenas.  Every rank must call integrate_async

@@ -399,14 +399,18 @@ fdem_status fdem_ipc_close(int32_t device, void* ptr);
  * distributed code; this is the B200-side answer to BASELINE.json's config 5.  Each rank holds
  * its stripe (fdem_map_create_stripe with the rows fastdem_b200/sharded.py's stripe_bounds gives
  * it), a FastDEM on it (GLOBAL mode) and one fdem_shard: the exchange arena every other rank maps
- * over CUDA IPC.  A scan is integrated in two halves per rank, on the map's stream:
- *   front: preprocessScan + binning of this rank's 1/world slice of the scan's points (read in
- *          place from wherever the scan lives — e.g. the ingest GPU's HBM, over NVLink) for
- *          EVERY stripe; the pre-reduced records stay in this rank's arena;
- *   back:  for every non-empty bucket of this rank's OWN stripe, pull its record pieces from all
- *          ranks' arenas (TMA bulk reads of peer memory) and run the per-cell estimator.
- * Device-side ready / consumed flags order the halves across ranks: no collective, no host round
- * trip.  Results are identical to one unsharded map (tests/test_gpu_shard.py).
+ * over CUDA IPC.  A scan is integrated in two halves per rank:
+ *   front (the mapper's side stream): preprocessScan + binning of this rank's SLICE of the scan's
+ *          points for EVERY stripe; each pre-reduced 32-byte record is stored straight into its
+ *          owner's arena (peer memory: NVLink stores).  The slice is decided on the device from
+ *          the stripes' loads two scans earlier — the same numbers on every rank, so the same
+ *          split — such that a rank whose stripe owns most of the touched cells (most of the
+ *          back half) bins few points or none;
+ *   back (the map's stream): for every non-empty bucket of this rank's OWN stripe, the per-cell
+ *          estimator over the records all sources pushed — local memory only.
+ * Device-side ready / consumed flags (system-scope release / acquire on words of the arenas)
+ * order the halves across ranks: no collective, no host round trip.  Results are identical to
+ * one unsharded map (tests/test_gpu_shard.py; tools/shard_parity.py on real GPUs).
  * Setup: create on every rank -> export -> exchange the handles out of band (e.g.
  * torch.distributed.all_gather_object) -> connect. */
 typedef struct fdem_shard fdem_shard;
@@ -420,12 +424,15 @@ fdem_status fdem_shard_connect(fdem_shard* shard, const fdem_ipc_handle* handles
  * EVERY rank calls it for every scan, in the same order, with the same scan: xyzw / intensity /
  * rgb address the WHOLE scan (n points) in device memory this rank can read; the scan must be
  * complete there when the call is made (the halves run on two streams and are not ordered behind
- * earlier work of the map's stream) and stay untouched until fdem_shard_wait has returned. */
+ * earlier work of the map's stream) and stay untouched until fdem_shard_wait has returned.
+ * Any rank may be handed most of a scan: give every rank a copy in its own HBM when NVLink reads
+ * of the scan would bound its K1 (sharded.PeerScanRing(replicated=True)). */
 fdem_status fdem_shard_integrate(fdem_shard* shard, const float* xyzw, const float* intensity,
                                  const uint8_t* rgb, size_t n, const double T_base_sensor[16],
                                  const double T_world_base[16]);
 /* waits for this rank's queued scans; stats of the newest as THIS rank saw it: n_kept = kept
- * points of its slice, n_cells = touched cells of its stripe (sum over ranks = scan totals) */
+ * points of its slice, n_cells = touched cells of its stripe (sum over ranks = scan totals),
+ * n_input = the whole scan */
 fdem_status fdem_shard_wait(fdem_shard* shard, fdem_scan_stats* stats);
 
 /* ── instrumentation ──────────────────────────────────────────────────────── */
