@@ -87,7 +87,8 @@ struct ScanResult {
 }  // namespace
 
 constexpr int kResultRing = 8;   // scans that may be in flight before a result slot is reused
-constexpr int kStageRing = 2;    // host-input staging buffers (copy of scan k+1 overlaps scan k)
+constexpr int kStageRing = 3;    // host-input staging buffers: the copies of scans k+1 and k+2 can be queued
+                                 // while scan k runs, so the copy engine never waits for the host's next submit
 
 struct fdem_map {
   int device = 0;
