@@ -151,6 +151,8 @@ SIGNATURES = {
     "fdem_shard_connect": (_ST, [_P, C.c_void_p]),
     "fdem_shard_integrate": (_ST, [_P, _f32p, _f32p, _u8p, C.c_size_t, _f64p, _f64p]),
     "fdem_shard_wait": (_ST, [_P, C.POINTER(FdemScanStats)]),
+    "fdem_shard_slice_plan": (_ST, [C.POINTER(C.c_uint32), C.c_int32, C.c_uint32, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "fdem_uncertainty_fusion": (_ST, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "fdem_feature_extraction": (_ST, [_P, C.c_float, C.c_int32, C.c_float, C.c_float]),
     "fdem_mapper_launch_count": (_ST, [_P, C.POINTER(C.c_int64)]),

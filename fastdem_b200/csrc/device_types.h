@@ -138,6 +138,56 @@ struct ShardSlice {
   uint32_t begin, count;
 };
 
+#if defined(__CUDACC__)
+#define FDEM_HOST_DEVICE __host__ __device__
+#else
+#define FDEM_HOST_DEVICE
+#endif
+// The slice of an n_scan-point scan that rank `rank` bins, given the cells each stripe's owner
+// touched (`load`).  Integer arithmetic only, identical on every rank and on the host
+// (fdem_shard_slice_plan).  A rank's work is (its share of the points) + w * (its share of the
+// cells), both as fractions in 1/65536, w = back_weight / 256 = the cost of a whole back half in
+// units of a whole front half; the shares of the points level that sum (water-filling): a rank
+// that owns most of the cells bins few points or none, the ranks with idle stripes bin the rest.
+// All loads zero: equal slices.  Boundaries are warp-aligned; slices tile [0, n_scan) in rank order.
+FDEM_HOST_DEVICE inline ShardSlice shard_slice_plan(const uint32_t* load, int world, int rank, uint32_t n_scan,
+                                                    uint32_t back_weight) {
+  uint32_t q[kMaxShards], share[kMaxShards];
+  uint64_t total = 0;
+  for (int d = 0; d < world; ++d) total += load[d];
+  constexpr uint32_t ONE = 65536u;
+  if (total == 0) {
+    for (int d = 0; d < world; ++d) share[d] = ONE / static_cast<uint32_t>(world);
+  } else {
+    for (int d = 0; d < world; ++d)
+      q[d] = static_cast<uint32_t>((static_cast<uint64_t>(load[d]) * ONE / total * back_weight) >> 8);
+    uint32_t active = (1u << world) - 1u, level = 0;
+    for (int it = 0; it < world; ++it) {
+      uint32_t sum = ONE, cnt = 0;
+      for (int d = 0; d < world; ++d)
+        if (active >> d & 1u) { sum += q[d]; ++cnt; }
+      level = sum / cnt;
+      uint32_t drop = 0;
+      for (int d = 0; d < world; ++d)
+        if ((active >> d & 1u) && q[d] > level) drop |= 1u << d;
+      if (!drop) break;
+      active &= ~drop;   // (the rank with the smallest load always stays)
+    }
+    for (int d = 0; d < world; ++d) share[d] = (active >> d & 1u) ? level - q[d] : 0u;
+  }
+  // cumulative shares scaled to the scan; the last rank with a share takes the rounding remainder
+  uint32_t acc = 0, total_share = 0;
+  for (int d = 0; d < world; ++d) total_share += share[d];
+  uint32_t b0 = 0, b1 = 0;
+  for (int d = 0; d <= rank; ++d) {
+    b0 = b1;
+    acc += share[d];
+    b1 = acc == total_share ? n_scan
+                            : static_cast<uint32_t>(static_cast<uint64_t>(n_scan) * acc / total_share) & ~31u;
+  }
+  return ShardSlice{b0, b1 - b0};
+}
+
 // one non-empty bucket of this rank's stripe: where its records lie in every source's arena
 struct ShardJob {
   uint32_t bucket;                   // bucket index inside the stripe

@@ -807,53 +807,14 @@ shard_begin_kernel(ShardHeader* __restrict__ hdr, uint32_t seq, int world, int r
   }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // ── this rank's slice of the scan ──
-    // Every owner published, with consumed[d] = seq - kShardDepth, how many cells of its stripe that scan
-    // touched: the same numbers on every rank, so every rank derives the same split, in integer
-    // arithmetic.  A rank's work is (its share of the points) + w * (its share of the cells),
-    // both as fractions in 1/65536, w = back_weight / 256 = the cost of a whole back half in
-    // units of a whole front half; the shares of the points level that sum (water-filling): a
-    // rank that owns most of the cells bins few points or none, the ranks with idle stripes bin
-    // the rest.  Before any load is known (first kShardDepth scans, or no cells at all): equal slices.
-    uint32_t q[kMaxShards], share[kMaxShards];
-    uint64_t total = 0;
-    for (int d = 0; d < world; ++d) {
-      q[d] = seq > kShardDepth ? ld_relaxed_sys(&hdr->load[seq % kShardDepth][d]) : 0u;
-      total += q[d];
-    }
-    constexpr uint32_t ONE = 65536u;
-    if (total == 0) {
-      for (int d = 0; d < world; ++d) share[d] = ONE / static_cast<uint32_t>(world);
-    } else {
-      for (int d = 0; d < world; ++d)
-        q[d] = static_cast<uint32_t>(static_cast<uint64_t>(q[d]) * ONE / total * back_weight >> 8);
-      uint32_t active = (1u << world) - 1u, level = 0;
-      for (int it = 0; it < world; ++it) {
-        uint32_t sum = ONE, cnt = 0;
-        for (int d = 0; d < world; ++d)
-          if (active >> d & 1u) { sum += q[d]; ++cnt; }
-        level = sum / cnt;
-        uint32_t drop = 0;
-        for (int d = 0; d < world; ++d)
-          if ((active >> d & 1u) && q[d] > level) drop |= 1u << d;
-        if (!drop) break;
-        active &= ~drop;   // (the rank with the smallest load always stays)
-      }
-      for (int d = 0; d < world; ++d) share[d] = (active >> d & 1u) ? level - q[d] : 0u;
-    }
-    // boundaries: cumulative shares scaled to the scan, warp-aligned; the last rank with a
-    // share takes the rounding remainder
-    uint32_t acc = 0, total_share = 0;
-    for (int d = 0; d < world; ++d) total_share += share[d];
-    uint32_t b0 = 0, b1 = 0;
-    for (int d = 0; d <= rank; ++d) {
-      b0 = b1;
-      acc += share[d];
-      b1 = acc == total_share ? n_scan
-                              : static_cast<uint32_t>(static_cast<uint64_t>(n_scan) * acc / total_share) & ~31u;
-    }
-    slice_out->begin = b0;
-    slice_out->count = b1 - b0;
+    // ── this rank's slice of the scan: every owner published, with consumed[d] = seq -
+    //    kShardDepth, how many cells of its stripe that scan touched — the same numbers on every
+    //    rank, so every rank derives the same split (shard_slice_plan, device_types.h).  Before
+    //    any load is known (the first kShardDepth scans): all zero = equal slices. ──
+    uint32_t load[kMaxShards];
+    for (int d = 0; d < world; ++d)
+      load[d] = seq > kShardDepth ? ld_relaxed_sys(&hdr->load[seq % kShardDepth][d]) : 0u;
+    *slice_out = shard_slice_plan(load, world, rank, n_scan, back_weight);
   }
   if (blockIdx.x == 0 && threadIdx.x < kFrontCounterWords) counters[threadIdx.x] = 0u;
 }

@@ -274,6 +274,21 @@ class ShardedGlobalMap:
             return eng.result("elevation_inpainted")
 
 
+def slice_plan(loads, n_points: int, back_weight_q8: int = 0):
+    """[(begin, count)] per rank: which points of an n_points scan each rank of a ShardedMapper
+    bins, given the cells every stripe's owner touched (fdem_shard_slice_plan — the rule the
+    front half applies on the device; pure host arithmetic, no GPU needed)."""
+    import ctypes as C
+    from . import capi
+    lib = capi.load_library()
+    world = len(loads)
+    arr = (C.c_uint32 * world)(*[int(x) for x in loads])
+    b = (C.c_uint32 * world)()
+    c = (C.c_uint32 * world)()
+    capi.check(lib.fdem_shard_slice_plan(arr, world, int(n_points), int(back_weight_q8), b, c))
+    return [(int(b[r]), int(c[r])) for r in range(world)]
+
+
 class ShardedMapper:
     """fastdem::FastDEM on ONE GLOBAL map row-striped over the ranks — the path whose compute
     scales with the rank count (fdem_shard_* in the C-ABI, protocol in csrc/device_types.h):

@@ -430,6 +430,13 @@ fdem_status fdem_shard_connect(fdem_shard* shard, const fdem_ipc_handle* handles
 fdem_status fdem_shard_integrate(fdem_shard* shard, const float* xyzw, const float* intensity,
                                  const uint8_t* rgb, size_t n, const double T_base_sensor[16],
                                  const double T_world_base[16]);
+/* The slice split of the front half, on the host (pure arithmetic, no GPU needed): given the
+ * cells each stripe's owner touched (loads[world]) it returns, for every rank, the first point
+ * and the number of points of an n_points scan that rank bins — slices tile [0, n_points) in rank
+ * order, boundaries are multiples of 32, ranks with busy stripes get fewer points.
+ * back_weight_q8 = cost of a whole back half in units of a whole front half, x256 (0 = default). */
+fdem_status fdem_shard_slice_plan(const uint32_t* loads, int32_t world, uint32_t n_points,
+                                  uint32_t back_weight_q8, uint32_t* begins, uint32_t* counts);
 /* waits for this rank's queued scans; stats of the newest as THIS rank saw it: n_kept = kept
  * points of its slice, n_cells = touched cells of its stripe (sum over ranks = scan totals),
  * n_input = the whole scan */

@@ -150,3 +150,65 @@ def test_sharded_map_two_ranks_gloo(tmp_path):
     assert np.array_equal(np.isnan(got["inpainted"]), np.isnan(want))
     assert np.allclose(np.nan_to_num(got["inpainted"]), np.nan_to_num(want), rtol=1e-6, atol=0)
     assert np.isfinite(want).sum() > np.isfinite(m.get("elevation")).sum()  # holes were filled
+
+
+# ── the load-aware slice split of the multi-GPU front half (fdem_shard_slice_plan: the same
+#    integer arithmetic shard_begin_kernel runs on the device) ──
+
+def _check_tiling(plan, n):
+    pos = 0
+    for b, c in plan:
+        assert b == pos, plan
+        pos += c
+    assert pos == n, plan
+    for b, c in plan[:-1]:
+        assert (b + c) % 32 == 0 or b + c == n, plan   # warp-aligned boundaries
+
+
+def test_slice_plan_equal_split_without_loads():
+    from fastdem_b200.sharded import slice_plan
+    n = 1048576
+    for world in (1, 2, 3, 4, 8):
+        plan = slice_plan([0] * world, n)
+        _check_tiling(plan, n)
+        counts = [c for _, c in plan]
+        assert max(counts) - min(counts) <= 64 + n % world, plan
+
+
+def test_slice_plan_busy_owner_bins_less():
+    from fastdem_b200.sharded import slice_plan
+    n = 1048576
+    # one stripe owns every touched cell: with a back half as dear as a front half it bins nothing
+    plan = slice_plan([102000, 0], n, back_weight_q8=256)
+    _check_tiling(plan, n)
+    assert plan[0][1] == 0 and plan[1][1] == n
+    # back half = half a front half: work levels at 0.75 each -> the owner bins a quarter
+    plan = slice_plan([102000, 0], n, back_weight_q8=128)
+    _check_tiling(plan, n)
+    assert abs(plan[0][1] / n - 0.25) < 1e-3
+    # eight ranks, three owners: owners bin least, the idle ranks share the rest equally
+    loads = [0, 0, 40000, 45000, 17000, 0, 0, 0]
+    plan = slice_plan(loads, n, back_weight_q8=256)
+    _check_tiling(plan, n)
+    counts = [c for _, c in plan]
+    idle = [counts[r] for r in range(8) if loads[r] == 0]
+    assert max(idle) - min(idle) <= 64 + 32 * 8          # rounding to warp boundaries only
+    assert counts[3] <= counts[2] <= counts[4] <= min(idle)   # more cells, fewer points
+    # level: points share + cells share is the same for every rank that bins anything
+    tot = sum(loads)
+    work = [counts[r] / n + loads[r] / tot for r in range(8) if counts[r] > 0]
+    assert max(work) - min(work) < 2e-3
+
+
+def test_slice_plan_is_deterministic_and_total_for_ragged_sizes():
+    from fastdem_b200.sharded import slice_plan
+    import random
+    rng = random.Random(7)
+    for _ in range(200):
+        world = rng.randint(1, 8)
+        n = rng.choice([1, 31, 32, 33, 1000, 28800, 131072, 1048576, 4000001])
+        loads = [rng.choice([0, 0, rng.randint(1, 200000)]) for _ in range(world)]
+        w = rng.choice([0, 1, 64, 128, 256, 1024, 4096])
+        a = slice_plan(loads, n, w)
+        assert a == slice_plan(loads, n, w)
+        _check_tiling(a, n)
