@@ -113,6 +113,22 @@ def test_sharded_mapper_matches_the_oracle(fdem, tmp_path, world):
     check_against_oracle(str(tmp_path), world, "tiny", 6)
 
 
+def test_sharded_mapper_one_rank_per_gpu(fdem, tmp_path):
+    """The real thing where the box has it: one rank per GPU, NCCL for the handle exchange, records
+    pushed over NVLink (tools/shard_parity.py is the same run as a script; on 2 x B200 it reports
+    0 bit-different cells for tiny, C2-sized and C5 scans).  Skipped on a one-GPU box — the
+    one-GPU worlds above run the same kernels and flags."""
+    import torch
+    n_gpus = torch.cuda.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(run_rank, args=(world, _free_port(), str(tmp_path), "tiny", 6, False, "nccl"),
+             nprocs=world, join=True)
+    assert check_against_oracle(str(tmp_path), world, "tiny", 6) == 0   # bit-identical cells
+
+
 def test_sharded_mapper_world_1_equals_plain_mapper(fdem, tmp_path):
     """Degenerate case in one process: the two-half pipeline against the one-GPU pipeline."""
     wl = syn.WORKLOADS["c1_vlp16_local"]
